@@ -1,0 +1,121 @@
+"""CPU restatement of the NanoSIMS MATLAB script's per-ROI reductions.
+
+TEST INFRASTRUCTURE ONLY.  Follows
+``HCN_nanosims_rois_activity_distance_5iso_YG.m``; MATLAB is not installed, so
+this restatement is pinned only against brute-force loops (parity unpinned by
+the reference).  Decisions the restatement had to take (SURVEY.md 8a caveats):
+
+* ROI numbering: MATLAB ``regionprops`` on a logical numbers 8-connected
+  components in COLUMN-major order of their first pixel (.m:104, :173) --
+  restated as raster-order labelling of the transposed mask.
+* ``imresize`` (.m:125) is the identity when the ROI image and the acquisition
+  have the same size, which is the only case the synthetic configs use.
+* Centroids are ``(x, y)`` = (column, row), 1-based (.m:164-165, :228-229).
+* Boundary pixels (``bwboundaries``, .m:290-291) are taken as the mask pixels with
+  a 4-neighbour outside the mask; they are ``(row, col)`` 1-based and are compared
+  with ``(x, y)`` centroids exactly as the script does (.m:301) -- a latent axis
+  swap in the reference that is reproduced, not fixed.
+"""
+
+import numpy as np
+from scipy import ndimage as ndi
+
+# .m:154 column order of the seven ion planes
+PLANES_7 = ("12C", "13C", "14N12C", "15N12C", "16O", "17O", "18O")
+# activity = plane[num] / sum(plane[den])   (.m:136-139)
+ACTIVITIES_7 = (("13C", (1, (1, 0))), ("15N", (3, (2, 3))), ("17O", (5, (6, 5, 4))), ("18O", (6, (6, 5, 4))))
+ACTIVITIES_5 = (("13C", (1, (1, 0))), ("15N", (3, (2, 3))))
+
+
+def matlab_label(mask):
+    """8-connected components numbered in column-major order (MATLAB ``bwconncomp``)."""
+    lab, n = ndi.label(np.ascontiguousarray(mask.T), structure=np.ones((3, 3)))
+    return np.ascontiguousarray(lab.T), n
+
+
+def roi_sums(planes, roi_labels, n_rois):
+    """.m:126-132, :190-196 -- ``sum(sum(plane .* roimask))`` for every plane and ROI."""
+    k = planes.shape[0]
+    out = np.zeros((n_rois, k), dtype=np.float64)
+    flat = roi_labels.ravel()
+    for j in range(k):
+        out[:, j] = np.bincount(flat, weights=planes[j].ravel(), minlength=n_rois + 1)[1 : n_rois + 1]
+    return out
+
+
+def activities(sums, spec):
+    """.m:136-139 -- isotope fractions from the per-ROI sums."""
+    cols = []
+    for _, (num, den) in spec:
+        d = np.zeros(len(sums))
+        for j in den:  # the script adds the planes left to right
+            d = d + sums[:, j]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            cols.append(sums[:, num] / d)
+    return np.column_stack(cols) if cols else np.zeros((len(sums), 0))
+
+
+def roi_centroids_xy(roi_labels, n_rois):
+    """.m:164-165 -- ``regionprops(roimask, 'Centroid')``: (x, y), 1-based."""
+    flat = roi_labels.ravel()
+    h, w = roi_labels.shape
+    yy, xx = np.divmod(np.arange(flat.size), w)
+    cnt = np.bincount(flat, minlength=n_rois + 1)[1 : n_rois + 1].astype(np.float64)
+    sy = np.bincount(flat, weights=yy, minlength=n_rois + 1)[1 : n_rois + 1]
+    sx = np.bincount(flat, weights=xx, minlength=n_rois + 1)[1 : n_rois + 1]
+    return np.column_stack([sx / cnt + 1.0, sy / cnt + 1.0])
+
+
+def nearest_between(a_xy, b_xy):
+    """.m:260-263 -- ``pdist2`` then the row / column minima."""
+    d = np.sqrt(((a_xy[:, None, :] - b_xy[None, :, :]) ** 2).sum(-1))
+    return d.min(axis=1), d.min(axis=0)
+
+
+def boundary_pixels(mask):
+    """.m:290-291 -- pixels of ``mask`` with a 4-neighbour outside it, (row, col) 1-based,
+    raster order."""
+    m = np.pad(mask.astype(bool), 1)
+    inner = m[1:-1, 1:-1]
+    all4 = m[:-2, 1:-1] & m[2:, 1:-1] & m[1:-1, :-2] & m[1:-1, 2:]
+    return np.argwhere(inner & ~all4).astype(np.float64) + 1.0
+
+
+def min_dist_to_points(xy, pts):
+    """.m:301-304 -- ``min(pdist2(positions, bd_position)')``."""
+    d2 = ((xy[:, None, :] - pts[None, :, :]) ** 2).sum(-1)
+    return np.sqrt(d2.min(axis=1))
+
+
+def analyse(planes, red_mask, green_mask, agg_mask, raster=19.0, acq=512.0):
+    """Whole-script restatement: rows ``[set, i, sums..., act..., act*100..., x, y,
+    nearest_um, boundary_um]`` for the red then the green ROIs
+    (.m:154, :216, :249-252, :265-268, :306-309)."""
+    k = planes.shape[0]
+    spec = ACTIVITIES_7 if k >= 7 else ACTIVITIES_5
+    rows, pos = [], []
+    for set_id, mask in ((1, red_mask), (2, green_mask)):
+        lab, n = matlab_label(mask)
+        s = roi_sums(planes, lab, n)
+        act = activities(s, spec)
+        xy = roi_centroids_xy(lab, n)
+        rows.append(np.column_stack([np.full(n, float(set_id)), np.arange(1, n + 1, dtype=np.float64), s, act, act * 100.0]))
+        pos.append(xy)
+    a_near, b_near = nearest_between(pos[0], pos[1])
+    bd = boundary_pixels(agg_mask)
+    scale = raster / acq  # ./(512/raster), .m:267, :308
+    near = np.concatenate([a_near, b_near]) * scale
+    bdist = np.concatenate([min_dist_to_points(pos[0], bd), min_dist_to_points(pos[1], bd)]) * scale
+    return np.column_stack([np.concatenate(rows), np.concatenate(pos), near, bdist])
+
+
+def activity_vs_distance(activity, distance, edges):
+    """north_star "activity-vs-distance binning" (no reference call site: the script
+    writes one CSV row per ROI).  ``np.digitize`` + ``np.bincount``: per bin the ROI
+    count, the activity sum and the mean."""
+    idx = np.digitize(distance, edges)
+    nb = len(edges) + 1
+    cnt = np.bincount(idx, minlength=nb).astype(np.float64)
+    tot = np.bincount(idx, weights=activity, minlength=nb)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return cnt, tot, tot / cnt
