@@ -1,0 +1,590 @@
+// K4 connected-component labelling and everything built on the same forest:
+// K6 fill holes, small-object removal, component selection, K9 plateau maxima.
+//
+// Replaces (file:line in /root/reference):
+//   skimage.measure.label            tiff_analysis.py:260, :743, :829; refine_boundaries.py:64
+//   scipy.ndimage.binary_fill_holes  tiff_analysis.py:880
+//   area filter on regions           tiff_analysis.py:769-773 (as skimage remove_small_objects)
+//   merged_image |= (labels == v)    tiff_analysis.py:878
+//   skimage.morphology.local_maxima  refine_boundaries.py:63
+#include "pcs_ccl.cuh"
+
+#include "pcs.h"
+
+#define PCS_CCL_THREADS 256
+#define PCS_MARK (-1)
+
+// ============================================================== workspace
+size_t pcs_ccl_ws_bytes(int B, int H, int W, int with_aux) {
+  size_t WW = pcs_words(W), Wp = WW * 32, CPR = (WW + 31) / 32;
+  size_t n = 0;
+  n += pcs_align256((size_t)B * H * Wp * 4);
+  n += pcs_align256((size_t)B * H * WW * 4);
+  n += pcs_align256((size_t)B * H * CPR * 4);
+  n += pcs_align256((size_t)(B + 1) * 4);
+  if (with_aux) n += pcs_align256((size_t)B * H * Wp * 4);
+  return n;
+}
+
+int pcs_ccl_ws_carve(void* ws, size_t ws_bytes, int B, int H, int W, int with_aux, PcsCclWs* out) {
+  if (ws == nullptr || ws_bytes < pcs_ccl_ws_bytes(B, H, W, with_aux)) {
+    pcs_set_error("connected-component workspace too small (see pcs_ccl_workspace_bytes)");
+    return PCS_ERR_WORKSPACE;
+  }
+  size_t WW = pcs_words(W), Wp = WW * 32, CPR = (WW + 31) / 32;
+  char* p = (char*)ws;
+  out->parent = (int*)p;
+  p += pcs_align256((size_t)B * H * Wp * 4);
+  out->rootbits = (uint32_t*)p;
+  p += pcs_align256((size_t)B * H * WW * 4);
+  out->chunk = (int*)p;
+  p += pcs_align256((size_t)B * H * CPR * 4);
+  out->offsets = (int*)p;
+  p += pcs_align256((size_t)(B + 1) * 4);
+  out->aux = with_aux ? (int*)p : nullptr;
+  return PCS_OK;
+}
+
+// ============================================================== kernels
+// thread per word: every run start becomes its own root
+template <class P>
+__global__ void __launch_bounds__(PCS_CCL_THREADS) k_ccl_init(P prov, int* __restrict__ parent, int B) {
+  const int H = prov.H, WW = prov.WW;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)B * H * WW;
+  if (t >= total) return;
+  int k = (int)(t % WW);
+  int y = (int)((t / WW) % H);
+  long long b = t / ((long long)WW * H);
+  P p = prov.slice(b);
+  uint32_t F, S;
+  p.FS(y, k, F, S);
+  if (!S) return;
+  const int Wp = WW << 5;
+  int* par = parent + b * (long long)H * Wp;
+  int base = y * Wp + (k << 5);
+  while (S) {
+    int s = __ffs(S) - 1;
+    S &= S - 1;
+    par[base + s] = base + s;
+  }
+}
+
+// thread per word: unite each run with the runs it touches in the row above and
+// with the run it continues from the previous word
+template <class P, int CONN>
+__global__ void __launch_bounds__(PCS_CCL_THREADS) k_ccl_merge(P prov, int* __restrict__ parent, int B) {
+  const int H = prov.H, WW = prov.WW;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)B * H * WW;
+  if (t >= total) return;
+  int k = (int)(t % WW);
+  int y = (int)((t / WW) % H);
+  long long b = t / ((long long)WW * H);
+  P p = prov.slice(b);
+  uint32_t F0, S0;
+  p.FS(y, k, F0, S0);
+  if (!F0) return;
+  PcsConnWords c;
+  p.conn(y, k, c);
+  const int Wp = WW << 5;
+  int* par = parent + b * (long long)H * Wp;
+  const int base = y * Wp + (k << 5);
+  if (c.J) {  // horizontal continuation across the word boundary
+    uint32_t Sl = p.Sword(y, k - 1);
+    int ls = 31 - __clz(Sl);
+    pcs_uf_union(par, base, base - 32 + ls);
+  }
+  if (y == 0) return;
+  if (!(c.U | c.UL | c.UR)) return;
+  uint32_t S = c.S;
+  const int abase = (y - 1) * Wp + (k << 5);
+  while (S) {
+    int s;
+    uint32_t R = pcs_pop_run(c.F, S, s);
+    // touch mask over the row above, bit i <-> x = 32k - 1 + i
+    unsigned long long T = ((unsigned long long)(c.U & R)) << 1;
+    if (CONN == 8) T |= (unsigned long long)(c.UL & R) | (((unsigned long long)(c.UR & R)) << 2);
+    while (T) {
+      int i = __ffsll((long long)T) - 1;
+      T &= T + (1ull << i);  // clear this run of consecutive touched pixels
+      int rel = (i - 1) >> 5;  // -1, 0, +1
+      int ja = (i - 1) & 31;
+      int sa = pcs_start_at_or_below(c.Sa[rel + 1], ja);
+      pcs_uf_union(par, base + s, abase + rel * 32 + sa);
+    }
+  }
+}
+
+// warp per 32-word chunk: point every node at its root, flag roots, count them
+template <class P>
+__global__ void __launch_bounds__(PCS_CCL_THREADS)
+    k_ccl_flatten(P prov, int* __restrict__ parent, uint32_t* __restrict__ rootbits, int* __restrict__ chunk,
+                  int* __restrict__ aux, int B, int CPR) {
+  const int H = prov.H, WW = prov.WW;
+  long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  long long total = (long long)B * H * CPR;
+  if (g >= total) return;
+  int ch = (int)(g % CPR);
+  int y = (int)((g / CPR) % H);
+  long long b = g / ((long long)CPR * H);
+  int k = ch * 32 + lane;
+  uint32_t roots = 0;
+  if (k < WW) {
+    P p = prov.slice(b);
+    uint32_t F, S;
+    p.FS(y, k, F, S);
+    const int Wp = WW << 5;
+    int* par = parent + b * (long long)H * Wp;
+    int base = y * Wp + (k << 5);
+    while (S) {
+      int s = __ffs(S) - 1;
+      S &= S - 1;
+      int n = base + s;
+      int r = n, q = pcs_ld_cg(par + r);
+      while (q != r) {
+        r = q;
+        q = pcs_ld_cg(par + r);
+      }
+      if (r != n)
+        par[n] = r;
+      else {
+        roots |= 1u << s;
+        if (aux) aux[b * (long long)H * Wp + n] = 0;
+      }
+    }
+    rootbits[(b * H + y) * (long long)WW + k] = roots;
+  }
+  int cnt = __popc(roots);
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if (lane == 0) chunk[g] = cnt;
+}
+
+// block per slice: exclusive scan of the chunk counts (raster order), slice total
+__global__ void __launch_bounds__(1024) k_ccl_scan(int* __restrict__ chunk, int32_t* __restrict__ counts, int n) {
+  __shared__ int wsum[32];
+  __shared__ int carry_s;
+  int* c = chunk + (long long)blockIdx.x * n;
+  int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += blockDim.x) {
+    int i = base + tid;
+    int v = i < n ? c[i] : 0;
+    int carry = carry_s;  // stable here: last written before the previous iteration's barriers
+    int tot;
+    int ex = pcs_warp_excl_scan(v, lane, &tot);
+    if (lane == 0) wsum[wid] = tot;
+    __syncthreads();
+    if (wid == 0) {
+      int w = lane < (int)(blockDim.x >> 5) ? wsum[lane] : 0;
+      int wt;
+      int wex = pcs_warp_excl_scan(w, lane, &wt);
+      wsum[lane] = wex;
+      if (lane == 0) carry_s = carry + wt;
+    }
+    __syncthreads();
+    if (i < n) c[i] = carry + wsum[wid] + ex;
+    __syncthreads();
+  }
+  if (tid == 0) counts[blockIdx.x] = carry_s;
+}
+
+// one block: exclusive scan of the per-slice counts -> table row offsets
+__global__ void __launch_bounds__(1024) k_ccl_offsets(const int32_t* __restrict__ counts, int* __restrict__ offsets, int B) {
+  __shared__ int wsum[32];
+  __shared__ int carry_s;
+  int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < B; base += blockDim.x) {
+    int i = base + tid;
+    int v = i < B ? counts[i] : 0;
+    int carry = carry_s;
+    int tot;
+    int ex = pcs_warp_excl_scan(v, lane, &tot);
+    if (lane == 0) wsum[wid] = tot;
+    __syncthreads();
+    if (wid == 0) {
+      int w = wsum[lane];
+      int wt;
+      int wex = pcs_warp_excl_scan(w, lane, &wt);
+      wsum[lane] = wex;
+      if (lane == 0) carry_s = carry + wt;
+    }
+    __syncthreads();
+    if (i < B) offsets[i] = carry + wsum[wid] + ex;
+    __syncthreads();
+  }
+  if (tid == 0) offsets[B] = carry_s;
+}
+
+// warp per chunk: roots get their raster-order rank (stored negated in parent),
+// and the table's first-pixel column if requested
+__global__ void __launch_bounds__(PCS_CCL_THREADS)
+    k_ccl_rank(int* __restrict__ parent, const uint32_t* __restrict__ rootbits, const int* __restrict__ chunk,
+               const int* __restrict__ offsets, long long* __restrict__ first_out, long long cap, int B, int H, int W,
+               int WW, int CPR) {
+  long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  long long total = (long long)B * H * CPR;
+  if (g >= total) return;
+  int ch = (int)(g % CPR);
+  int y = (int)((g / CPR) % H);
+  long long b = g / ((long long)CPR * H);
+  int k = ch * 32 + lane;
+  uint32_t roots = k < WW ? rootbits[(b * H + y) * (long long)WW + k] : 0u;
+  int tot;
+  int ex = pcs_warp_excl_scan(__popc(roots), lane, &tot);
+  if (!roots) return;
+  int rank = chunk[g] + ex;
+  const int Wp = WW << 5;
+  int* par = parent + b * (long long)H * Wp;
+  int base = y * Wp + (k << 5);
+  long long trow = first_out ? (long long)offsets[b] : 0;
+  while (roots) {
+    int s = __ffs(roots) - 1;
+    roots &= roots - 1;
+    ++rank;
+    par[base + s] = -rank;
+    if (first_out) {
+      long long row = trow + rank - 1;
+      if (row < cap) first_out[row] = (long long)y * W + (k << 5) + s;
+    }
+  }
+}
+
+__device__ __forceinline__ int pcs_label_of(const int* par, int node) {
+  int p = par[node];
+  return p < 0 ? -p : -par[p];
+}
+
+// warp per chunk: expand run labels to pixels with coalesced 128-byte stores
+template <class P, typename OutT>
+__global__ void __launch_bounds__(PCS_CCL_THREADS)
+    k_ccl_relabel(P prov, const int* __restrict__ parent, OutT* __restrict__ out, int B, int CPR) {
+  __shared__ int lab[PCS_CCL_THREADS / 32][32][33];
+  const int H = prov.H, WW = prov.WW, W = prov.W;
+  long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+  long long total = (long long)B * H * CPR;
+  if (g >= total) return;
+  int ch = (int)(g % CPR);
+  int y = (int)((g / CPR) % H);
+  long long b = g / ((long long)CPR * H);
+  int k = ch * 32 + lane;
+  uint32_t F = 0, S = 0;
+  const int Wp = WW << 5;
+  const int* par = parent + b * (long long)H * Wp;
+  if (k < WW) {
+    P p = prov.slice(b);
+    p.FS(y, k, F, S);
+    int base = y * Wp + (k << 5);
+    uint32_t rem = S;
+    while (rem) {  // four independent lookups in flight per iteration
+      int s0 = __ffs(rem) - 1;
+      rem &= rem - 1;
+      int s1 = rem ? __ffs(rem) - 1 : -1;
+      rem &= rem - 1 + (rem == 0);
+      int s2 = rem ? __ffs(rem) - 1 : -1;
+      rem &= rem - 1 + (rem == 0);
+      int s3 = rem ? __ffs(rem) - 1 : -1;
+      rem &= rem - 1 + (rem == 0);
+      int p0 = par[base + s0];
+      int p1 = s1 >= 0 ? par[base + s1] : -1;
+      int p2 = s2 >= 0 ? par[base + s2] : -1;
+      int p3 = s3 >= 0 ? par[base + s3] : -1;
+      int l0 = p0 < 0 ? -p0 : -par[p0];
+      int l1 = p1 < 0 ? -p1 : -par[p1];
+      int l2 = p2 < 0 ? -p2 : -par[p2];
+      int l3 = p3 < 0 ? -p3 : -par[p3];
+      lab[wl][lane][s0] = l0;
+      if (s1 >= 0) lab[wl][lane][s1] = l1;
+      if (s2 >= 0) lab[wl][lane][s2] = l2;
+      if (s3 >= 0) lab[wl][lane][s3] = l3;
+    }
+  }
+  __syncwarp();
+  OutT* orow = out + (b * H + y) * (long long)W;
+  int nk = min(32, WW - ch * 32);
+  for (int kk = 0; kk < nk; ++kk) {
+    uint32_t f = __shfl_sync(0xffffffffu, F, kk);
+    uint32_t s = __shfl_sync(0xffffffffu, S, kk);
+    int x = ((ch * 32 + kk) << 5) + lane;
+    int v = 0;
+    if ((f >> lane) & 1u) v = lab[wl][kk][pcs_start_at_or_below(s, lane)];
+    if (x < W) orow[x] = (OutT)v;
+  }
+}
+
+// thread per word: mark the roots of runs selected by `mode`
+//   mode 0: runs touching the image border       (fill holes)
+//   mode 1: runs intersecting the bit plane `m`  (seeds / higher-neighbour flags)
+template <class P>
+__global__ void __launch_bounds__(PCS_CCL_THREADS)
+    k_ccl_mark(P prov, int* __restrict__ parent, const uint32_t* __restrict__ m, int mode, int B) {
+  const int H = prov.H, WW = prov.WW, W = prov.W;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)B * H * WW;
+  if (t >= total) return;
+  int k = (int)(t % WW);
+  int y = (int)((t / WW) % H);
+  long long b = t / ((long long)WW * H);
+  P p = prov.slice(b);
+  uint32_t F, S;
+  p.FS(y, k, F, S);
+  if (!S) return;
+  uint32_t M;
+  if (mode == 0) {
+    M = (y == 0 || y == H - 1) ? 0xffffffffu : 0u;
+    if (k == 0) M |= 1u;
+    if (k == WW - 1) M |= 1u << ((W - 1) & 31);
+  } else {
+    M = m[t];
+  }
+  M &= F;
+  if (!M) return;
+  const int Wp = WW << 5;
+  int* par = parent + b * (long long)H * Wp;
+  int base = y * Wp + (k << 5);
+  while (S) {
+    int s;
+    uint32_t R = pcs_pop_run(F, S, s);
+    if (!(R & M)) continue;
+    int n = base + s;
+    int q = par[n];
+    if (q < 0) continue;  // already a marked root
+    par[q] = PCS_MARK;     // q is the root (q == n for a root)
+  }
+}
+
+// thread per word: accumulate run lengths at the roots
+template <class P>
+__global__ void __launch_bounds__(PCS_CCL_THREADS) k_ccl_area(P prov, const int* __restrict__ parent, int* __restrict__ aux, int B) {
+  const int H = prov.H, WW = prov.WW;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)B * H * WW;
+  if (t >= total) return;
+  int k = (int)(t % WW);
+  int y = (int)((t / WW) % H);
+  long long b = t / ((long long)WW * H);
+  P p = prov.slice(b);
+  uint32_t F, S;
+  p.FS(y, k, F, S);
+  if (!S) return;
+  const int Wp = WW << 5;
+  const int* par = parent + b * (long long)H * Wp;
+  int* ax = aux + b * (long long)H * Wp;
+  int base = y * Wp + (k << 5);
+  while (S) {
+    int s;
+    uint32_t R = pcs_pop_run(F, S, s);
+    atomicAdd(ax + par[base + s], __popc(R));
+  }
+}
+
+// thread per word: mark roots whose accumulated area is below min_size
+__global__ void __launch_bounds__(PCS_CCL_THREADS)
+    k_ccl_mark_small(int* __restrict__ parent, const uint32_t* __restrict__ rootbits, const int* __restrict__ aux,
+                     int min_size, int B, int H, int WW) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)B * H * WW;
+  if (t >= total) return;
+  uint32_t roots = rootbits[t];
+  if (!roots) return;
+  int k = (int)(t % WW);
+  int y = (int)((t / WW) % H);
+  long long b = t / ((long long)WW * H);
+  const int Wp = WW << 5;
+  long long sb = b * (long long)H * Wp;
+  int base = y * Wp + (k << 5);
+  while (roots) {
+    int s = __ffs(roots) - 1;
+    roots &= roots - 1;
+    if (aux[sb + base + s] < min_size) parent[sb + base + s] = PCS_MARK;
+  }
+}
+
+// thread per word: out = runs whose root is marked (want=1) / unmarked (want=0),
+// optionally OR-ed with another bit plane; all-or-nothing veto by counts==1
+template <class P>
+__global__ void __launch_bounds__(PCS_CCL_THREADS)
+    k_ccl_select(P prov, const int* __restrict__ parent, int want_marked, const uint32_t* __restrict__ or_bits,
+                 const int32_t* __restrict__ veto_counts, uint32_t* __restrict__ out, int B) {
+  const int H = prov.H, WW = prov.WW;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)B * H * WW;
+  if (t >= total) return;
+  int k = (int)(t % WW);
+  int y = (int)((t / WW) % H);
+  long long b = t / ((long long)WW * H);
+  P p = prov.slice(b);
+  uint32_t F, S;
+  p.FS(y, k, F, S);
+  uint32_t o = 0;
+  if (S && !(veto_counts && veto_counts[b] == 1)) {
+    const int Wp = WW << 5;
+    const int* par = parent + b * (long long)H * Wp;
+    int base = y * Wp + (k << 5);
+    while (S) {
+      int s;
+      uint32_t R = pcs_pop_run(F, S, s);
+      int n = base + s;
+      int q = par[n];
+      int marked = q < 0 ? 1 : (q == n ? 0 : (par[q] < 0));
+      if (marked == want_marked) o |= R;
+    }
+  }
+  if (or_bits) o |= or_bits[t];
+  out[t] = o;
+}
+
+// ============================================================== host drivers
+template <class P>
+static int ccl_forest(const P& prov, int B, int conn, const PcsCclWs& ws, int32_t* counts, int zero_aux, cudaStream_t st) {
+  const int H = prov.H, WW = prov.WW;
+  const int CPR = (WW + 31) / 32;
+  long long words = (long long)B * H * WW;
+  long long warps = (long long)B * H * CPR;
+  unsigned gw = pcs_blocks(words, PCS_CCL_THREADS);
+  unsigned gc = pcs_blocks(warps * 32, PCS_CCL_THREADS);
+  k_ccl_init<P><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, B);
+  if (conn == 8)
+    k_ccl_merge<P, 8><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, B);
+  else
+    k_ccl_merge<P, 4><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, B);
+  k_ccl_flatten<P><<<gc, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, ws.rootbits, ws.chunk, zero_aux ? ws.aux : nullptr, B, CPR);
+  if (counts) {
+    k_ccl_scan<<<B, 1024, 0, st>>>(ws.chunk, counts, H * CPR);
+    k_ccl_offsets<<<1, 1024, 0, st>>>(counts, ws.offsets, B);
+  }
+  return pcs_check_launch("ccl forest");
+}
+
+template <class P>
+static int ccl_label(const P& prov, int B, int conn, void* labels, int label_bytes, int32_t* counts, int32_t* offsets_out,
+                     long long* first_out, long long cap, void* wsp, size_t ws_bytes, cudaStream_t st) {
+  PCS_REQUIRE(conn == 4 || conn == 8, "connectivity must be 4 or 8");
+  PCS_REQUIRE(label_bytes == 4 || label_bytes == 8, "label dtype must be int32 or int64");
+  PCS_REQUIRE(counts != nullptr && labels != nullptr, "null output");
+  PcsCclWs ws;
+  int rc = pcs_ccl_ws_carve(wsp, ws_bytes, B, prov.H, prov.W, 0, &ws);
+  if (rc) return rc;
+  rc = ccl_forest(prov, B, conn, ws, counts, 0, st);
+  if (rc) return rc;
+  const int H = prov.H, WW = prov.WW, CPR = (WW + 31) / 32;
+  unsigned gc = pcs_blocks((long long)B * H * CPR * 32, PCS_CCL_THREADS);
+  k_ccl_rank<<<gc, PCS_CCL_THREADS, 0, st>>>(ws.parent, ws.rootbits, ws.chunk, ws.offsets, first_out, cap, B, H, prov.W, WW, CPR);
+  if (label_bytes == 4)
+    k_ccl_relabel<P, int32_t><<<gc, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, (int32_t*)labels, B, CPR);
+  else
+    k_ccl_relabel<P, long long><<<gc, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, (long long*)labels, B, CPR);
+  if (offsets_out) cudaMemcpyAsync(offsets_out, ws.offsets, (size_t)(B + 1) * 4, cudaMemcpyDeviceToDevice, st);
+  return pcs_check_launch("ccl label");
+}
+
+static int check_dims(int B, int H, int W) {
+  PCS_REQUIRE(B >= 1 && H >= 1 && W >= 1, "empty batch or image");
+  PCS_REQUIRE(H <= 16384 && W <= 16384, "image side above 16384 is not supported");
+  return PCS_OK;
+}
+
+extern "C" {
+
+size_t pcs_ccl_workspace_bytes(int B, int H, int W, int with_aux) { return pcs_ccl_ws_bytes(B, H, W, with_aux); }
+
+int pcs_label_bits(const uint32_t* bits, int B, int H, int W, int connectivity, int invert, void* labels, int label_bytes,
+                   int32_t* counts, int32_t* offsets, int64_t* first_out, int64_t cap, void* ws, size_t ws_bytes,
+                   void* stream) {
+  int rc = check_dims(B, H, W);
+  if (rc) return rc;
+  PcsBinProv prov{bits, H, W, pcs_words(W), invert};
+  return ccl_label(prov, B, connectivity, labels, label_bytes, counts, offsets, (long long*)first_out, cap, ws, ws_bytes,
+                   (cudaStream_t)stream);
+}
+
+int pcs_label_conn(const uint32_t* planes, int B, int H, int W, int connectivity, void* labels, int label_bytes,
+                   int32_t* counts, int32_t* offsets, int64_t* first_out, int64_t cap, void* ws, size_t ws_bytes,
+                   void* stream) {
+  int rc = check_dims(B, H, W);
+  if (rc) return rc;
+  PcsGenProv prov{planes, (long long)B * H * pcs_words(W), H, W, pcs_words(W)};
+  return ccl_label(prov, B, connectivity, labels, label_bytes, counts, offsets, (long long*)first_out, cap, ws, ws_bytes,
+                   (cudaStream_t)stream);
+}
+
+int pcs_fill_holes_bits(const uint32_t* bits, uint32_t* out, int B, int H, int W, void* wsp, size_t ws_bytes, void* stream) {
+  int rc = check_dims(B, H, W);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  PcsCclWs ws;
+  rc = pcs_ccl_ws_carve(wsp, ws_bytes, B, H, W, 0, &ws);
+  if (rc) return rc;
+  PcsBinProv prov{bits, H, W, pcs_words(W), 1};  // background, 4-connected (tiff_analysis.py:880)
+  rc = ccl_forest(prov, B, 4, ws, nullptr, 0, st);
+  if (rc) return rc;
+  unsigned gw = pcs_blocks((long long)B * H * prov.WW, PCS_CCL_THREADS);
+  k_ccl_mark<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, nullptr, 0, B);
+  k_ccl_select<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, 0, bits, nullptr, out, B);
+  return pcs_check_launch("fill holes");
+}
+
+int pcs_remove_small_bits(const uint32_t* bits, uint32_t* out, int B, int H, int W, int connectivity, int min_size,
+                          void* wsp, size_t ws_bytes, void* stream) {
+  int rc = check_dims(B, H, W);
+  if (rc) return rc;
+  PCS_REQUIRE(connectivity == 4 || connectivity == 8, "connectivity must be 4 or 8");
+  cudaStream_t st = (cudaStream_t)stream;
+  PcsCclWs ws;
+  rc = pcs_ccl_ws_carve(wsp, ws_bytes, B, H, W, 1, &ws);
+  if (rc) return rc;
+  PcsBinProv prov{bits, H, W, pcs_words(W), 0};
+  rc = ccl_forest(prov, B, connectivity, ws, nullptr, 1, st);
+  if (rc) return rc;
+  unsigned gw = pcs_blocks((long long)B * H * prov.WW, PCS_CCL_THREADS);
+  k_ccl_area<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, ws.aux, B);
+  k_ccl_mark_small<<<gw, PCS_CCL_THREADS, 0, st>>>(ws.parent, ws.rootbits, ws.aux, min_size, B, H, prov.WW);
+  k_ccl_select<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, 0, nullptr, nullptr, out, B);
+  return pcs_check_launch("remove small objects");
+}
+
+int pcs_select_components_bits(const uint32_t* bits, const uint32_t* seeds, uint32_t* out, int B, int H, int W,
+                               int connectivity, void* wsp, size_t ws_bytes, void* stream) {
+  int rc = check_dims(B, H, W);
+  if (rc) return rc;
+  PCS_REQUIRE(connectivity == 4 || connectivity == 8, "connectivity must be 4 or 8");
+  cudaStream_t st = (cudaStream_t)stream;
+  PcsCclWs ws;
+  rc = pcs_ccl_ws_carve(wsp, ws_bytes, B, H, W, 0, &ws);
+  if (rc) return rc;
+  PcsBinProv prov{bits, H, W, pcs_words(W), 0};
+  rc = ccl_forest(prov, B, connectivity, ws, nullptr, 0, st);
+  if (rc) return rc;
+  unsigned gw = pcs_blocks((long long)B * H * prov.WW, PCS_CCL_THREADS);
+  k_ccl_mark<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, seeds, 1, B);
+  k_ccl_select<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, 1, nullptr, nullptr, out, B);
+  return pcs_check_launch("select components");
+}
+
+int pcs_local_maxima_conn(const uint32_t* planes, const uint32_t* higher, uint32_t* out, int32_t* counts, int B, int H,
+                          int W, int connectivity, void* wsp, size_t ws_bytes, void* stream) {
+  int rc = check_dims(B, H, W);
+  if (rc) return rc;
+  PCS_REQUIRE(connectivity == 4 || connectivity == 8, "connectivity must be 4 or 8");
+  PCS_REQUIRE(counts != nullptr, "null counts");
+  cudaStream_t st = (cudaStream_t)stream;
+  PcsCclWs ws;
+  rc = pcs_ccl_ws_carve(wsp, ws_bytes, B, H, W, 0, &ws);
+  if (rc) return rc;
+  PcsGenProv prov{planes, (long long)B * H * pcs_words(W), H, W, pcs_words(W)};
+  rc = ccl_forest(prov, B, connectivity, ws, counts, 0, st);
+  if (rc) return rc;
+  unsigned gw = pcs_blocks((long long)B * H * prov.WW, PCS_CCL_THREADS);
+  k_ccl_mark<PcsGenProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, higher, 1, B);
+  // a plateau that is the whole image (counts == 1) is not a maximum
+  k_ccl_select<PcsGenProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, 0, nullptr, counts, out, B);
+  return pcs_check_launch("local maxima");
+}
+
+}  // extern "C"

@@ -1,0 +1,70 @@
+// Shared device/host helpers for libpcs (sm_100a).
+//
+// Data model used by every kernel in this library:
+//   * images are batches of independent 2-D slices, shape (B, H, W), C order
+//     (split_zstack.py:52 iterates slices; tiff_analysis.py:727-737 only ever
+//     processes 2-D images), one launch covers the whole batch;
+//   * binary masks travel as BIT ROWS: uint32 words, WW = ceil(W/32) words per
+//     row, bit j of word k is pixel x = 32*k + j; bits at x >= W are always 0;
+//   * connected-component nodes are the starts of within-word runs, addressed
+//     in the padded index space  node = y * (32*WW) + x  (raster order kept).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define PCS_OK 0
+#define PCS_ERR_INVALID (-1)
+#define PCS_ERR_CUDA (-2)
+#define PCS_ERR_WORKSPACE (-3)
+#define PCS_ERR_UNSUPPORTED (-4)
+
+extern "C" void pcs_set_error(const char* msg);
+int pcs_check_launch(const char* what);
+
+#define PCS_REQUIRE(cond, msg)        \
+  do {                                \
+    if (!(cond)) {                    \
+      pcs_set_error(msg);             \
+      return PCS_ERR_INVALID;         \
+    }                                 \
+  } while (0)
+
+static inline int pcs_words(int W) { return (W + 31) >> 5; }
+static inline size_t pcs_align256(size_t n) { return (n + 255) & ~(size_t)255; }
+static inline unsigned pcs_blocks(long long n, int per_block) {
+  long long b = (n + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  if (b > 0x7fffffffLL) b = 0x7fffffffLL;
+  return (unsigned)b;
+}
+
+// ---------------------------------------------------------------- device helpers
+__device__ __forceinline__ uint32_t pcs_valid_mask(int k, int W) {
+  // valid-pixel mask of word k in a row of W pixels
+  int rem = W - (k << 5);
+  return rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+}
+
+__device__ __forceinline__ int pcs_ld_cg(const int* p) { return __ldcg(p); }
+
+// start bit of the within-word run of `w` that contains bit j (bit j must be set)
+__device__ __forceinline__ int pcs_run_start(uint32_t w, int j) {
+  uint32_t zeros_below = ~w & ((1u << j) - 1u);
+  return zeros_below ? 32 - __clz(zeros_below) : 0;
+}
+// highest set bit of s at or below j (s must have one)
+__device__ __forceinline__ int pcs_start_at_or_below(uint32_t s, int j) {
+  uint32_t m = s & (0xffffffffu >> (31 - j));
+  return 31 - __clz(m);
+}
+
+__device__ __forceinline__ int pcs_warp_excl_scan(int v, int lane, int* total) {
+  int x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += t;
+  }
+  *total = __shfl_sync(0xffffffffu, x, 31);
+  return x - v;
+}

@@ -1,0 +1,210 @@
+// K5 binary morphology on bit rows (flat footprint as horizontal runs) and
+// K3 median filtering (uint8 images, and the binary majority special case).
+//
+// Replaces (file:line in /root/reference):
+//   skimage.morphology.binary_dilation(mask, disk(2))   tiff_analysis.py:827-828
+//   skimage.morphology.binary_dilation(mask, disk(20))  tiff_analysis.py:990 (via pcs_edt_bits)
+//   scipy.ndimage.median_filter(ds_arr, size=5)         tiff_analysis.py:122, :643
+// plus erosion / opening / closing (north_star; no reference call site) by duality:
+//   erode(X, S, border) = ~dilate(~X, reflect(S), !border).
+#include "pcs_common.cuh"
+
+#include "pcs.h"
+
+#define MORPH_THREADS 256
+
+struct PcsRun {
+  int dy, lo, hi;  // offsets covered: (dy, dx) for dx in [lo, hi], hi - lo + 1 <= 32
+};
+
+// out(y, x) = OR over runs, dx in [lo, hi] of in'(y - dy, x - dx), in' = in ^ invert_in,
+// pixels outside the image read as `border`.
+__global__ void __launch_bounds__(MORPH_THREADS)
+    k_dilate_bits(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const PcsRun* __restrict__ runs, int n_runs,
+                  int invert_in, int border, int invert_out, int B, int H, int W, int WW) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)B * H * WW;
+  if (t >= total) return;
+  const int k = (int)(t % WW);
+  const int y = (int)((t / WW) % H);
+  const long long b = t / ((long long)WW * H);
+  const uint32_t* src = in + b * (long long)H * WW;
+  const uint32_t bw = border ? 0xffffffffu : 0u;
+  uint32_t acc = 0;
+  for (int r = 0; r < n_runs; ++r) {
+    const PcsRun run = runs[r];
+    const int ys = y - run.dy;
+    const int len = run.hi - run.lo + 1;
+    const bool row_out = ys < 0 || ys >= H;
+    // source word j smears onto x in [32j + lo, 32j + lo + 30 + len]; keep those meeting word k
+    const int jmax = ((k << 5) + 31 - run.lo) >> 5;
+    const int jmin = ((k << 5) - run.lo - len + 1) >> 5;  // arithmetic shift = floor
+    for (int j = jmin; j <= jmax; ++j) {
+      uint32_t w;
+      if (row_out || j < 0 || j >= WW) {
+        w = bw;
+      } else {
+        w = __ldg(src + (long long)ys * WW + j);
+        const uint32_t vm = pcs_valid_mask(j, W);
+        if (invert_in) w = ~w;
+        w = (w & vm) | (bw & ~vm);
+      }
+      if (!w) continue;
+      unsigned long long S = w;
+      int cover = 1;
+      while (cover * 2 <= len) {
+        S |= S << cover;
+        cover *= 2;
+      }
+      if (len > cover) S |= S << (len - cover);
+      const int sft = 32 * (k - j) - run.lo;  // out bit t <- S bit (t + sft)
+      uint32_t c;
+      if (sft >= 0)
+        c = sft < 64 ? (uint32_t)(S >> sft) : 0u;
+      else
+        c = -sft < 32 ? ((uint32_t)S) << (-sft) : 0u;
+      acc |= c;
+    }
+  }
+  const uint32_t vm = pcs_valid_mask(k, W);
+  out[t] = (invert_out ? ~acc : acc) & vm;
+}
+
+// ---------------------------------------------------------------- median
+__device__ __forceinline__ int pcs_reflect(int i, int n) {
+  // scipy.ndimage mode='reflect': (d c b a | a b c d | d c b a)
+  if (i < 0) i = -i - 1;
+  if (i >= n) i = 2 * n - i - 1;
+  return i;
+}
+
+__device__ __forceinline__ uint32_t pcs_getbit(const uint32_t* row, int x) { return (row[x >> 5] >> (x & 31)) & 1u; }
+
+// 64-bit window of a bit row: window bit i <-> x = 32k - 16 + i, reflected at the row ends
+__device__ __forceinline__ unsigned long long pcs_window_reflect(const uint32_t* row, int k, int W, int WW, int r) {
+  unsigned long long win = (unsigned long long)row[k] << 16;
+  if (k > 0) win |= row[k - 1] >> 16;
+  if (k + 1 < WW) win |= (unsigned long long)(row[k + 1] & 0xffffu) << 48;
+  if (k == 0)
+    for (int q = 1; q <= r; ++q) win |= (unsigned long long)pcs_getbit(row, q - 1) << (16 - q);
+  const int xhi = (k << 5) + 47;
+  if (xhi >= W)
+    for (int q = 1; q <= r; ++q) {
+      int x = W - 1 + q;
+      int i = x - (k << 5) + 16;
+      if (i >= 0 && i < 64) win |= (unsigned long long)pcs_getbit(row, W - q) << i;
+    }
+  return win;
+}
+
+// binary median (majority) of a size x size window, mode reflect; thread per word
+template <int size>
+__global__ void __launch_bounds__(MORPH_THREADS)
+    k_majority_bits(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int B, int H, int W, int WW) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)B * H * WW;
+  if (t >= total) return;
+  const int k = (int)(t % WW);
+  const int y = (int)((t / WW) % H);
+  const long long b = t / ((long long)WW * H);
+  const uint32_t* src = in + b * (long long)H * WW;
+  const int r = size >> 1;
+  const int need = (size * size) / 2 + 1;  // ones needed for the median to be 1
+  const uint32_t wm = (1u << size) - 1u;
+  unsigned long long win[size];
+#pragma unroll
+  for (int dy = -r; dy <= r; ++dy) win[dy + r] = pcs_window_reflect(src + (long long)pcs_reflect(y + dy, H) * WW, k, W, WW, r);
+  uint32_t o = 0;
+  for (int tb = 0; tb < 32; ++tb) {
+    int cnt = 0;
+#pragma unroll
+    for (int q = 0; q < size; ++q) cnt += __popc((uint32_t)(win[q] >> (tb + 16 - r)) & wm);
+    o |= (uint32_t)(cnt >= need) << tb;
+  }
+  out[t] = o & pcs_valid_mask(k, W);
+}
+
+// generic uint8 median, size in {3, 5, 7}, mode reflect; CTA tile 32 x 8 with halo in shared memory
+#define MED_TX 32
+#define MED_TY 8
+template <int size>
+__global__ void __launch_bounds__(MED_TX* MED_TY)
+    k_median_u8(const uint8_t* __restrict__ img, uint8_t* __restrict__ out, int H, int W) {
+  __shared__ uint8_t tile[MED_TY + 6][MED_TX + 6 + 2];
+  const int r = size >> 1;
+  const int rank = (size * size) / 2;
+  const long long b = blockIdx.z;
+  const uint8_t* src = img + b * (long long)H * W;
+  const int x0 = blockIdx.x * MED_TX, y0 = blockIdx.y * MED_TY;
+  const int tw = MED_TX + 2 * r, th = MED_TY + 2 * r;
+  for (int i = threadIdx.y * MED_TX + threadIdx.x; i < tw * th; i += MED_TX * MED_TY) {
+    int ty = i / tw, tx = i % tw;
+    int yy = pcs_reflect(y0 + ty - r, H), xx = pcs_reflect(x0 + tx - r, W);
+    tile[ty][tx] = src[(long long)yy * W + xx];
+  }
+  __syncthreads();
+  const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+  if (x >= W || y >= H) return;
+  // largest v with #(window < v) <= rank is the rank-th smallest value
+  int v = 0;
+  for (int bit = 7; bit >= 0; --bit) {
+    const int cand = v | (1 << bit);
+    int cnt = 0;
+#pragma unroll
+    for (int dy = 0; dy < size; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < size; ++dx) cnt += tile[threadIdx.y + dy][threadIdx.x + dx] < cand;
+    if (cnt <= rank) v = cand;
+  }
+  out[b * (long long)H * W + (long long)y * W + x] = (uint8_t)v;
+}
+
+extern "C" {
+
+int pcs_dilate_bits(const uint32_t* in, uint32_t* out, const int32_t* runs, int n_runs, int invert_in, int border,
+                    int invert_out, int B, int H, int W, void* stream) {
+  PCS_REQUIRE(B >= 1 && H >= 1 && W >= 1, "empty batch or image");
+  PCS_REQUIRE(n_runs >= 1 && runs != nullptr, "empty footprint");
+  PCS_REQUIRE(in != out, "dilation cannot run in place");
+  int WW = pcs_words(W);
+  k_dilate_bits<<<pcs_blocks((long long)B * H * WW, MORPH_THREADS), MORPH_THREADS, 0, (cudaStream_t)stream>>>(
+      in, out, (const PcsRun*)runs, n_runs, invert_in, border, invert_out, B, H, W, WW);
+  return pcs_check_launch("dilate");
+}
+
+int pcs_majority_bits(const uint32_t* in, uint32_t* out, int size, int B, int H, int W, void* stream) {
+  PCS_REQUIRE(B >= 1 && H >= 1 && W >= 1, "empty batch or image");
+  PCS_REQUIRE(size == 3 || size == 5 || size == 7, "median size must be 3, 5 or 7");
+  PCS_REQUIRE(H >= size && W >= size, "image smaller than the median window");
+  PCS_REQUIRE(in != out, "median cannot run in place");
+  int WW = pcs_words(W);
+  unsigned g = pcs_blocks((long long)B * H * WW, MORPH_THREADS);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (size == 3)
+    k_majority_bits<3><<<g, MORPH_THREADS, 0, st>>>(in, out, B, H, W, WW);
+  else if (size == 5)
+    k_majority_bits<5><<<g, MORPH_THREADS, 0, st>>>(in, out, B, H, W, WW);
+  else
+    k_majority_bits<7><<<g, MORPH_THREADS, 0, st>>>(in, out, B, H, W, WW);
+  return pcs_check_launch("majority");
+}
+
+int pcs_median_u8(const uint8_t* img, uint8_t* out, int size, int B, int H, int W, void* stream) {
+  PCS_REQUIRE(B >= 1 && H >= 1 && W >= 1, "empty batch or image");
+  PCS_REQUIRE(size == 3 || size == 5 || size == 7, "median size must be 3, 5 or 7");
+  PCS_REQUIRE(H >= size && W >= size, "image smaller than the median window");
+  PCS_REQUIRE(img != out, "median cannot run in place");
+  PCS_REQUIRE(B <= 65535, "batch above 65535");
+  dim3 grid((W + MED_TX - 1) / MED_TX, (H + MED_TY - 1) / MED_TY, B);
+  dim3 block(MED_TX, MED_TY);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (size == 3)
+    k_median_u8<3><<<grid, block, 0, st>>>(img, out, H, W);
+  else if (size == 5)
+    k_median_u8<5><<<grid, block, 0, st>>>(img, out, H, W);
+  else
+    k_median_u8<7><<<grid, block, 0, st>>>(img, out, H, W);
+  return pcs_check_launch("median");
+}
+
+}  // extern "C"

@@ -1,0 +1,176 @@
+"""Z-stack layout (``split_zstack.py``) and the full per-slice segment pipeline.
+
+``split_zstack.py:50-65`` reads a ``(Z, C, Y, X)`` TIFF stack and writes every
+``z_slice[channel]`` plane to its own file; ilastik (an external GUI classifier)
+then turns the planes into class images for ``tiff_analysis.py``.  Here the same
+layout contract feeds the device pipeline directly:
+
+    threshold (Otsu)  ->  5x5 median  ->  label  ->  regionprops
+                      ->  refine (small objects out, holes filled)  ->  EDT
+
+Each stage is the library call the reference makes at the cited line (or, for
+Otsu / small-object removal, the one the north_star names); the CPU statement of
+the same composition is ``oracle/pipeline.py``.  Every slice is an independent
+2-D problem (tiff_analysis.py:727-737), so a stack is processed as batched
+kernel launches over chunks of slices and shards across GPUs by slice with no
+halo (``dist.py``).
+"""
+
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _io, _lib, ops
+
+CHANNEL_MAP_4 = {0: "CY5", 1: "RFP", 2: "GFP", 3: "DAPI"}  # split_zstack.py:39
+CHANNEL_MAP_2 = {0: "RFP", 1: "GFP"}  # split_zstack.py:54
+
+TABLE_COLUMNS = ("z", "label", "area", "centroid_y", "centroid_x", "min_row", "min_col", "max_row", "max_col", "first_row", "first_col", "intensity_sum", "intensity_mean")
+
+
+def split_channels(zstack, channel_indices=(1, 2)):
+    """split_zstack.py:52-65 without the file I/O: ``{channel name: (Z, Y, X) planes}``.
+    A stack whose slices do not have 4 channels is treated as ``RFP, GFP`` (:53-55)."""
+    if zstack.ndim != 4:
+        raise ValueError(f"expected a (Z, C, Y, X) stack, got {zstack.shape}")
+    cmap = CHANNEL_MAP_4
+    if zstack.shape[1] != 4:
+        cmap, channel_indices = CHANNEL_MAP_2, (0, 1)
+    return {cmap[c]: zstack[:, c] for c in channel_indices}
+
+
+def plane_name(base, z, channel):
+    """File name the reference would give the plane (split_zstack.py:63)."""
+    return f"{base}_z{z}_{channel}.tif"
+
+
+@dataclass
+class SegmentResult:
+    """Device-resident outputs of ``segment_zstack_device`` (16 B / voxel)."""
+
+    mask: torch.Tensor  # (Z, H, W) uint8
+    labels: torch.Tensor  # (Z, H, W) int32
+    refined: torch.Tensor  # (Z, H, W) uint8
+    edt: torch.Tensor  # (Z, H, W) float64
+    threshold: torch.Tensor  # (Z,) int32
+    counts: torch.Tensor  # (Z,) int32
+    tables: list = field(default_factory=list)  # per chunk: (z0, offsets[B+1], int64 table)
+    z0: int = 0
+
+    def table_device(self):
+        """Compact ``(n, 13)`` float64 table on the device (one sync to learn the sizes)."""
+        parts = []
+        H, W = self.labels.shape[1:]
+        for z0, offsets, table in self.tables:
+            off = offsets.cpu().numpy().astype(np.int64)
+            n = int(off[-1])
+            if n > table.shape[1]:
+                raise _lib.PcsError(f"region table overflow: {n} regions in a chunk, capacity {table.shape[1]}; raise max_regions_per_slice")
+            if n == 0:
+                continue
+            t = table[:, :n].to(torch.float64)
+            z = torch.repeat_interleave(torch.arange(len(off) - 1, device=table.device, dtype=torch.float64) + float(z0 + self.z0), torch.as_tensor(np.diff(off), device=table.device))
+            lab = torch.arange(n, device=table.device, dtype=torch.float64) - torch.repeat_interleave(torch.as_tensor(off[:-1], device=table.device, dtype=torch.float64), torch.as_tensor(np.diff(off), device=table.device)) + 1.0
+            area = t[ops.T_AREA]
+            first = table[ops.T_FIRST, :n]
+            cols = [z, lab, area, t[ops.T_SUMY] / area, t[ops.T_SUMX] / area, t[ops.T_MINY], t[ops.T_MINX], t[ops.T_MAXY] + 1.0, t[ops.T_MAXX] + 1.0,
+                    torch.div(first, W, rounding_mode="floor").to(torch.float64), (first % W).to(torch.float64), t[ops.T_SUMI], t[ops.T_SUMI] / area]
+            parts.append(torch.stack(cols, dim=1))
+        if not parts:
+            return torch.zeros((0, len(TABLE_COLUMNS)), dtype=torch.float64, device=self.labels.device)
+        return torch.cat(parts, dim=0)
+
+    def to_numpy(self):
+        return {
+            "threshold": self.threshold.cpu().numpy().astype(np.int64),
+            "mask": self.mask.cpu().numpy().astype(bool),
+            "labels": self.labels.cpu().numpy(),
+            "refined": self.refined.cpu().numpy().astype(bool),
+            "edt": self.edt.cpu().numpy(),
+            "table": self.table_device().cpu().numpy(),
+            "counts": self.counts.cpu().numpy().astype(np.int64),
+        }
+
+
+def segment_zstack_device(stack, denoise_size=5, min_size=20, chunk=16, max_regions_per_slice=1 << 16, out=None, z0=0):
+    """Full pipeline over a device-resident ``(Z, H, W)`` uint16 stack.
+
+    Asynchronous on the current stream; no host synchronisation inside.  ``out`` may
+    carry preallocated output tensors (a previous ``SegmentResult``) to reuse.
+    """
+    ops.require_cuda(stack, "stack")
+    if stack.dtype != torch.uint16 or stack.dim() != 3:
+        raise _lib.PcsError(f"segment_zstack_device expects a (Z, H, W) uint16 tensor, got {tuple(stack.shape)} {stack.dtype}")
+    Z, H, W = (int(s) for s in stack.shape)
+    dev = stack.device
+    if out is None:
+        out = SegmentResult(
+            mask=torch.empty((Z, H, W), dtype=torch.uint8, device=dev),
+            labels=torch.empty((Z, H, W), dtype=torch.int32, device=dev),
+            refined=torch.empty((Z, H, W), dtype=torch.uint8, device=dev),
+            edt=torch.empty((Z, H, W), dtype=torch.float64, device=dev),
+            threshold=torch.empty(Z, dtype=torch.int32, device=dev),
+            counts=torch.empty(Z, dtype=torch.int32, device=dev),
+        )
+    out.tables = []
+    out.z0 = z0
+    lib = _lib.load()
+    st = ops._stream()
+    P = ops._p
+    for a in range(0, Z, chunk):
+        b = min(Z, a + chunk)
+        B = b - a
+        img = stack[a:b]
+        WW = ops.words(W)
+        # K1: histogram + Otsu, K2: threshold, K3: 5x5 median of the binary image
+        hist = torch.empty((B, 65536), dtype=torch.int32, device=dev)
+        thr = out.threshold[a:b]
+        _lib.check(lib.pcs_histogram_u16(P(img), P(hist), B, H, W, st), "histogram")
+        _lib.check(lib.pcs_otsu_u16(P(hist), P(thr), 0, B, H * W, st), "otsu")
+        raw = torch.empty((B, H, WW), dtype=torch.int32, device=dev)
+        _lib.check(lib.pcs_compare_u16(P(img), 0, P(thr), 0, P(raw), 0, B, H, W, st), "threshold")
+        if denoise_size and denoise_size > 1:
+            bits = torch.empty_like(raw)
+            _lib.check(lib.pcs_majority_bits(P(raw), P(bits), denoise_size, B, H, W, st), "median")
+        else:
+            bits = raw
+        _lib.check(lib.pcs_unpack_bits(P(bits), P(out.mask[a:b]), B, H, W, st), "mask out")
+        # K4: labels (8-connected, raster order), K8: per-label table
+        labels = out.labels[a:b]
+        counts = out.counts[a:b]
+        offsets = torch.empty(B + 1, dtype=torch.int32, device=dev)
+        nws = lib.pcs_ccl_workspace_bytes(B, H, W, 0)
+        ws = ops._ws(nws, dev, "ccl")
+        _lib.check(lib.pcs_label_bits(P(bits), B, H, W, 8, 0, P(labels), 4, P(counts), P(offsets), 0, 0, P(ws), nws, st), "label")
+        table = ops.new_table(max_regions_per_slice * B, dev)
+        ops.region_table(labels, offsets, table, intensity=img, fg_bits=bits)
+        # refine: small objects out (area from the table), holes filled
+        keep = ops.select_by_area(labels, bits, table, offsets, min_size) if min_size and min_size > 1 else bits
+        refined_bits = torch.empty_like(keep)
+        _lib.check(lib.pcs_fill_holes_bits(P(keep), P(refined_bits), B, H, W, P(ws), nws, st), "fill holes")
+        _lib.check(lib.pcs_unpack_bits(P(refined_bits), P(out.refined[a:b]), B, H, W, st), "refined out")
+        # K7: exact EDT of the refined mask
+        nwe = lib.pcs_edt_workspace_bytes(B, H, W)
+        wse = ops._ws(nwe, dev, "edt")
+        _lib.check(lib.pcs_edt_bits(P(refined_bits), 0, B, H, W, P(out.edt[a:b]), 0, 0, 0, P(wse), nwe, st), "edt")
+        out.tables.append((a, offsets, table))
+    return out
+
+
+def segment_zstack(stack, denoise_size=5, min_size=20, chunk=16, max_regions_per_slice=1 << 16, z0=0):
+    """numpy ``(Z, H, W)`` (or a single ``(H, W)`` slice) in, dict of numpy arrays out:
+    ``threshold, mask, labels, refined, edt, table, counts`` -- the same keys and dtypes
+    as ``oracle.pipeline.segment_zstack``."""
+    np_in = _io.is_numpy(stack)
+    t = _io.to_device(stack)
+    single = t.dim() == 2
+    if single:
+        t = t.unsqueeze(0)
+    res = segment_zstack_device(t, denoise_size, min_size, chunk, max_regions_per_slice, z0=z0)
+    if not np_in:
+        return res
+    d = res.to_numpy()
+    if single:
+        d = {k: (v[0] if k not in ("table",) else v) for k, v in d.items()}
+    return d
