@@ -1,0 +1,364 @@
+#!/usr/bin/env python3
+"""Benchmark of the segmentation hot path (BASELINE.json metric: Mvoxel/s of the full
+segment pipeline, % of the HBM roofline, CPU reference beside it).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU path (oracle port)
+
+One "step" = one pass of threshold -> median -> label -> regionprops -> refine -> EDT
+over one synthetic (Z, 2048, 2048) uint16 z-stack per GPU (BASELINE.json configs[1]:
+Z = 64).  Weak scaling: every rank owns its own stack; the only exchange is the
+gather of the per-label tables.  Rank 0 prints ONE JSON line.
+"""
+
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "Mvoxel/s full segment pipeline (threshold->label->refine->EDT->regionprops)"
+PIPELINE_BYTES_PER_VOXEL = 16.0  # u16 in 2 + mask 1 + labels 4 + refined 1 + EDT f64 8
+SUM_OF_STAGES_BYTES_PER_VOXEL = 27.0
+# algorithmic bytes per voxel of each kernel (DESIGN.md section "Kernels"): inputs that must be
+# read once + outputs that must be written once, bit images counted as 1/8 B
+KERNEL_BYTES_PER_VOXEL = {
+    "k_hist_u16": 2.0,
+    "k_compare": 2.0 + 0.125,
+    "k_majority_bits": 0.25,
+    "k_unpack": 1.0 + 0.125,
+    "k_ccl_init": 0.125,
+    "k_ccl_merge": 0.125,
+    "k_ccl_flatten": 0.125,
+    "k_ccl_rank": 0.125,
+    "k_ccl_relabel": 4.0 + 0.125,
+    "k_ccl_mark": 0.125,
+    "k_ccl_select": 0.25,
+    "k_region_table": 4.0 + 2.0,
+    "k_select_by_area": 0.25,
+    "k_edt_cols": 2.0 + 0.125,
+    "k_edt_rows": 8.0 + 2.0,
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--slices", type=int, default=64, help="slices per GPU (configs[1]: 64; north_star target: 256)")
+    ap.add_argument("--size", type=int, default=2048)
+    ap.add_argument("--chunk", type=int, default=16, help="slices per batched launch")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="slices in the CPU baseline sample (0 = one per host core, at most 32)")
+    ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------- CPU reference arm
+_SAMPLE = None
+
+
+def _cpu_one(i):
+    from oracle import pipeline as opipe
+
+    t = time.perf_counter()
+    r = opipe.segment_slice(_SAMPLE[i])
+    return time.perf_counter() - t, int(r["labels"].max())
+
+
+def cpu_reference(size, n_sample, steps=1, warmup=0):
+    """Times the oracle (the reference's scipy / scikit-image composition) on host cores.
+    Returns (Mvoxel/s, cores used, description, ms per step)."""
+    import multiprocessing as mp
+
+    from particle_col_image_segmentation_b200 import synth
+
+    global _SAMPLE
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, n_sample))
+    _SAMPLE = synth.zstack_u16(n_sample, size, size, seed=1002)
+    ctx = mp.get_context("fork")  # workers inherit the sample; CUDA is not initialised yet
+    with ctx.Pool(procs) as pool:
+        for _ in range(warmup):
+            pool.map(_cpu_one, range(n_sample), chunksize=1)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            pool.map(_cpu_one, range(n_sample), chunksize=1)
+        dt = (time.perf_counter() - t0) / steps
+    _SAMPLE = None
+    mvox = n_sample * size * size / dt / 1e6
+    return mvox, procs, f"{n_sample} slices of the {size}x{size} uint16 stack (seed 1002), one process per slice on {procs} of {cores} host cores", dt * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_sample = args.cpu_sample or max(1, min(cores, 32))
+    mvox, procs, desc, ms = cpu_reference(args.size, n_sample, steps=args.steps, warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": mvox,
+        "unit": "Mvoxel/s",
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": min(args.warmup, 1),
+        "ms_per_step": ms,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "u16",
+        "data": "synthetic",
+        "config": {"workload": f"split_zstack + segment a synthetic {args.size}x{args.size}x{args.slices} uint16 z-stack (configs[1]); each step = a bounded sample of {n_sample} slices", "size": args.size, "slices": args.slices},
+        "cpu_baseline": {"value": mvox, "unit": "Mvoxel/s", "cores": procs, "kind": "port", "sample": desc},
+        "e2e": {"value": mvox, "unit": "Mvoxel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference = the repo's own scipy/scikit-image call sequence (oracle port; scikit-image calls restated, it is not installable offline); no C/C++ reference sources exist, so oracle/_ref does not apply",
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------- clocks
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.ok, self.stop_flag = [], set(), False, False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:  # noqa: BLE001
+            self.max_mhz = None
+
+    def _loop(self):
+        while not self.stop_flag:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                try:
+                    r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.05)
+
+    def start(self):
+        if self.ok:
+            self.th = threading.Thread(target=self._loop, daemon=True)
+            self.th.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.ok:
+            self.th.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------- CUDA arm
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json, copy bandwidth)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def collect_profile(lib):
+    names = ctypes.create_string_buffer(64 * 64)
+    ms = (ctypes.c_double * 64)()
+    cnt = (ctypes.c_int32 * 64)()
+    n = lib.pcs_profile_collect(ctypes.cast(names, ctypes.c_void_p), ctypes.cast(ms, ctypes.c_void_p), ctypes.cast(cnt, ctypes.c_void_p), 64)
+    out = {}
+    for i in range(n):
+        out[names.raw[64 * i : 64 * i + 64].split(b"\0")[0].decode()] = (ms[i], cnt[i])
+    return out
+
+
+def run_b200(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    Z, S = args.slices, args.size
+
+    cpu = None
+    if rank == 0 and args.gpus == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        n_sample = args.cpu_sample or max(1, min(cores, 32))
+        mvox, procs, desc, _ = cpu_reference(S, n_sample)  # before CUDA is initialised (fork)
+        cpu = {"value": mvox, "unit": "Mvoxel/s", "cores": procs, "kind": "port", "sample": desc}
+
+    import torch
+    import torch.distributed as dist
+
+    from oracle import pipeline as opipe
+    from particle_col_image_segmentation_b200 import _lib, split_zstack, synth
+    from particle_col_image_segmentation_b200 import dist as pdist
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    stack = synth.zstack_u16_device(Z, S, S, seed=1002 + rank, device=dev)
+    res = None
+
+    def step():
+        nonlocal res
+        res = split_zstack.segment_zstack_device(stack, chunk=args.chunk, out=res, z0=rank * Z)
+        table = res.table_device()
+        if world > 1:
+            table = pdist.gather_tables(table)
+        return table
+
+    # parity spot check against the oracle on one slice of this very stack (outside the timed region)
+    parity = None
+    if rank == 0:
+        table = step()
+        torch.cuda.synchronize()
+        zi = Z // 2
+        want = opipe.segment_slice(stack[zi].cpu().numpy(), z=zi)
+        got_tab = table[table[:, 0] == zi].cpu().numpy()
+        parity = bool(
+            int(res.threshold[zi]) == want["threshold"]
+            and np.array_equal(res.mask[zi].cpu().numpy().astype(bool), want["mask"])
+            and np.array_equal(res.labels[zi].cpu().numpy(), want["labels"])
+            and np.array_equal(res.refined[zi].cpu().numpy().astype(bool), want["refined"])
+            and np.array_equal(res.edt[zi].cpu().numpy(), want["edt"])
+            and np.array_equal(got_tab, want["table"])
+        )
+        if not parity:
+            raise SystemExit("bench: CUDA pipeline differs from the oracle on the spot-check slice; refusing to time it")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = lib.pcs_kernel_launches()
+    if not args.no_profile:
+        lib.pcs_profile_enable(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        table = step()
+    e1.record()
+    barrier()
+    lib.pcs_profile_enable(0)
+    launches = lib.pcs_kernel_launches() - launches0
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    voxels = float(Z) * S * S * world
+    value = voxels / (ms_step * 1e-3) / 1e6
+
+    prof = {} if args.no_profile else collect_profile(lib)
+
+    # end to end through the public API with host buffers (pinned), copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        host_in = torch.empty((Z, S, S), dtype=torch.uint16).pin_memory()
+        host_in.copy_(stack)
+        host_out = split_zstack.alloc_host_outputs(Z, S, S)
+        split_zstack.segment_zstack_pinned(host_in, host_out, chunk=args.chunk)  # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            nrows = split_zstack.segment_zstack_pinned(host_in, host_out, chunk=args.chunk)
+        barrier()
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        d2h = sum(v.numel() * v.element_size() for k, v in host_out.items() if k != "table") + nrows * 13 * 8
+        e2e = {"value": voxels / float(tt.item()) / 1e6, "unit": "Mvoxel/s", "h2d_bytes_per_step": host_in.numel() * 2, "d2h_bytes_per_step": int(d2h), "ms_per_step": float(tt.item()) * 1e3}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    roof = None
+    shares = {}
+    if prof:
+        tot = sum(v[0] for v in prof.values())
+        shares = {k: round(v[0] / tot, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
+        name, (kms, kcnt) = max(prof.items(), key=lambda kv: kv[1][0])
+        per_launch_vox = float(min(args.chunk, Z)) * S * S  # every launch covers one chunk of slices
+        bpv = KERNEL_BYTES_PER_VOXEL.get(name, PIPELINE_BYTES_PER_VOXEL)
+        avg_ms = kms / kcnt
+        achieved = bpv * per_launch_vox / (avg_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "bytes_per_voxel": bpv, "avg_launch_ms": avg_ms, "launches": kcnt, "peak_source": peak_src, "kernel_time_share": shares}
+    per_gpu = value / world * 1e6
+    line = {
+        "metric": METRIC,
+        "value": value,
+        "unit": "Mvoxel/s",
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": ms_step,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "u16",
+        "data": "synthetic",
+        "config": {"workload": f"split_zstack + segment a synthetic {S}x{S}x{Z} uint16 z-stack per GPU (BASELINE.json configs[1])", "size": S, "slices_per_gpu": Z, "chunk": args.chunk,
+                   "l2": "input stack (%.0f MiB) and outputs are larger than L2; no flush needed" % (Z * S * S * 2 / 2**20), "parity_spot_check": parity},
+        "clocks": clocks,
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "pipeline_roofline": {"bytes_per_voxel": PIPELINE_BYTES_PER_VOXEL, "achieved_gbs_per_gpu": per_gpu * PIPELINE_BYTES_PER_VOXEL / 1e9, "frac_of_peak": per_gpu * PIPELINE_BYTES_PER_VOXEL / 1e9 / peak,
+                              "sum_of_stages_frac": per_gpu * SUM_OF_STAGES_BYTES_PER_VOXEL / 1e9 / peak},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -34,6 +34,11 @@ extern "C" {
 int pcs_version(void);
 const char* pcs_last_error_string(void);
 int pcs_device_sm_count(int device);
+/* launch accounting: kernels launched since load; optional per-kernel CUDA-event timing on the
+ * launching stream (enable, run, collect -> distinct kernel names (64-char slots), total ms, launches) */
+uint64_t pcs_kernel_launches(void);
+int pcs_profile_enable(int on);
+int pcs_profile_collect(char* names, double* total_ms, int32_t* launches, int n_max); /* host pointers */
 
 /* ---- K2: thresholds, class masks, LUT relabels --------------------------------
  * cmp: 0 '>', 1 '>=', 2 '<', 3 '<=', 4 '==', 5 '!='.  thr_dev (optional) holds one

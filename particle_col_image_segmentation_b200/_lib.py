@@ -26,6 +26,9 @@ SIGNATURES = {
     "pcs_version": (c_int, []),
     "pcs_last_error_string": (c_char_p, []),
     "pcs_device_sm_count": (c_int, [_I]),
+    "pcs_kernel_launches": (c_uint64, []),
+    "pcs_profile_enable": (c_int, [_I]),
+    "pcs_profile_collect": (c_int, [_P, _P, _P, _I]),
     "pcs_compare_u8": (c_int, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _P]),
     "pcs_compare_u16": (c_int, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _P]),
     "pcs_compare_i32": (c_int, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _P]),

@@ -449,15 +449,15 @@ static int ccl_forest(const P& prov, int B, int conn, const PcsCclWs& ws, int32_
   long long warps = (long long)B * H * CPR;
   unsigned gw = pcs_blocks(words, PCS_CCL_THREADS);
   unsigned gc = pcs_blocks(warps * 32, PCS_CCL_THREADS);
-  k_ccl_init<P><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, B);
+  PCS_LAUNCH("k_ccl_init", st, k_ccl_init<P><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, B));
   if (conn == 8)
-    k_ccl_merge<P, 8><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, B);
+    PCS_LAUNCH("k_ccl_merge", st, k_ccl_merge<P, 8><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, B));
   else
-    k_ccl_merge<P, 4><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, B);
-  k_ccl_flatten<P><<<gc, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, ws.rootbits, ws.chunk, zero_aux ? ws.aux : nullptr, B, CPR);
+    PCS_LAUNCH("k_ccl_merge", st, k_ccl_merge<P, 4><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, B));
+  PCS_LAUNCH("k_ccl_flatten", st, k_ccl_flatten<P><<<gc, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, ws.rootbits, ws.chunk, zero_aux ? ws.aux : nullptr, B, CPR));
   if (counts) {
-    k_ccl_scan<<<B, 1024, 0, st>>>(ws.chunk, counts, H * CPR);
-    k_ccl_offsets<<<1, 1024, 0, st>>>(counts, ws.offsets, B);
+    PCS_LAUNCH("k_ccl_scan", st, k_ccl_scan<<<B, 1024, 0, st>>>(ws.chunk, counts, H * CPR));
+    PCS_LAUNCH("k_ccl_offsets", st, k_ccl_offsets<<<1, 1024, 0, st>>>(counts, ws.offsets, B));
   }
   return pcs_check_launch("ccl forest");
 }
@@ -475,11 +475,11 @@ static int ccl_label(const P& prov, int B, int conn, void* labels, int label_byt
   if (rc) return rc;
   const int H = prov.H, WW = prov.WW, CPR = (WW + 31) / 32;
   unsigned gc = pcs_blocks((long long)B * H * CPR * 32, PCS_CCL_THREADS);
-  k_ccl_rank<<<gc, PCS_CCL_THREADS, 0, st>>>(ws.parent, ws.rootbits, ws.chunk, ws.offsets, first_out, cap, B, H, prov.W, WW, CPR);
+  PCS_LAUNCH("k_ccl_rank", st, k_ccl_rank<<<gc, PCS_CCL_THREADS, 0, st>>>(ws.parent, ws.rootbits, ws.chunk, ws.offsets, first_out, cap, B, H, prov.W, WW, CPR));
   if (label_bytes == 4)
-    k_ccl_relabel<P, int32_t><<<gc, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, (int32_t*)labels, B, CPR);
+    PCS_LAUNCH("k_ccl_relabel", st, k_ccl_relabel<P, int32_t><<<gc, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, (int32_t*)labels, B, CPR));
   else
-    k_ccl_relabel<P, long long><<<gc, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, (long long*)labels, B, CPR);
+    PCS_LAUNCH("k_ccl_relabel", st, k_ccl_relabel<P, long long><<<gc, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, (long long*)labels, B, CPR));
   if (offsets_out) cudaMemcpyAsync(offsets_out, ws.offsets, (size_t)(B + 1) * 4, cudaMemcpyDeviceToDevice, st);
   return pcs_check_launch("ccl label");
 }
@@ -525,8 +525,8 @@ int pcs_fill_holes_bits(const uint32_t* bits, uint32_t* out, int B, int H, int W
   rc = ccl_forest(prov, B, 4, ws, nullptr, 0, st);
   if (rc) return rc;
   unsigned gw = pcs_blocks((long long)B * H * prov.WW, PCS_CCL_THREADS);
-  k_ccl_mark<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, nullptr, 0, B);
-  k_ccl_select<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, 0, bits, nullptr, out, B);
+  PCS_LAUNCH("k_ccl_mark", st, k_ccl_mark<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, nullptr, 0, B));
+  PCS_LAUNCH("k_ccl_select", st, k_ccl_select<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, 0, bits, nullptr, out, B));
   return pcs_check_launch("fill holes");
 }
 
@@ -543,9 +543,9 @@ int pcs_remove_small_bits(const uint32_t* bits, uint32_t* out, int B, int H, int
   rc = ccl_forest(prov, B, connectivity, ws, nullptr, 1, st);
   if (rc) return rc;
   unsigned gw = pcs_blocks((long long)B * H * prov.WW, PCS_CCL_THREADS);
-  k_ccl_area<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, ws.aux, B);
-  k_ccl_mark_small<<<gw, PCS_CCL_THREADS, 0, st>>>(ws.parent, ws.rootbits, ws.aux, min_size, B, H, prov.WW);
-  k_ccl_select<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, 0, nullptr, nullptr, out, B);
+  PCS_LAUNCH("k_ccl_area", st, k_ccl_area<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, ws.aux, B));
+  PCS_LAUNCH("k_ccl_mark_small", st, k_ccl_mark_small<<<gw, PCS_CCL_THREADS, 0, st>>>(ws.parent, ws.rootbits, ws.aux, min_size, B, H, prov.WW));
+  PCS_LAUNCH("k_ccl_select", st, k_ccl_select<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, 0, nullptr, nullptr, out, B));
   return pcs_check_launch("remove small objects");
 }
 
@@ -562,8 +562,8 @@ int pcs_select_components_bits(const uint32_t* bits, const uint32_t* seeds, uint
   rc = ccl_forest(prov, B, connectivity, ws, nullptr, 0, st);
   if (rc) return rc;
   unsigned gw = pcs_blocks((long long)B * H * prov.WW, PCS_CCL_THREADS);
-  k_ccl_mark<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, seeds, 1, B);
-  k_ccl_select<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, 1, nullptr, nullptr, out, B);
+  PCS_LAUNCH("k_ccl_mark", st, k_ccl_mark<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, seeds, 1, B));
+  PCS_LAUNCH("k_ccl_select", st, k_ccl_select<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, 1, nullptr, nullptr, out, B));
   return pcs_check_launch("select components");
 }
 
@@ -581,9 +581,9 @@ int pcs_local_maxima_conn(const uint32_t* planes, const uint32_t* higher, uint32
   rc = ccl_forest(prov, B, connectivity, ws, counts, 0, st);
   if (rc) return rc;
   unsigned gw = pcs_blocks((long long)B * H * prov.WW, PCS_CCL_THREADS);
-  k_ccl_mark<PcsGenProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, higher, 1, B);
+  PCS_LAUNCH("k_ccl_mark", st, k_ccl_mark<PcsGenProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, higher, 1, B));
   // a plateau that is the whole image (counts == 1) is not a maximum
-  k_ccl_select<PcsGenProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, 0, nullptr, counts, out, B);
+  PCS_LAUNCH("k_ccl_select", st, k_ccl_select<PcsGenProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, 0, nullptr, counts, out, B));
   return pcs_check_launch("local maxima");
 }
 

@@ -20,6 +20,15 @@
 
 extern "C" void pcs_set_error(const char* msg);
 int pcs_check_launch(const char* what);
+// launch accounting / optional per-kernel CUDA-event timing (pcs_profile_* in pcs.h)
+void pcs_prof_begin(const char* name, cudaStream_t st);
+void pcs_prof_end(cudaStream_t st);
+#define PCS_LAUNCH(name, st, ...)  \
+  do {                             \
+    pcs_prof_begin(name, st);      \
+    __VA_ARGS__;                   \
+    pcs_prof_end(st);              \
+  } while (0)
 
 #define PCS_REQUIRE(cond, msg)        \
   do {                                \

@@ -118,10 +118,13 @@ __global__ void __launch_bounds__(EDT_ROW_THREADS)
   for (int x0 = 0; x0 < Wp; x0 += EDT_ROW_THREADS) {
     const int x = x0 + tid;
     long long d2 = 0;
+    bool nosite = false;
     if (x < W) {
       const uint32_t a = am[x];
       if (a == EDT_INF) {
-        // no background pixel anywhere: scipy measures to the virtual point (-1, 0)
+        // no background pixel anywhere: scipy measures to the virtual point (-1, 0);
+        // for the threshold output (dilation of an empty mask) the distance is infinite
+        nosite = true;
         d2 = (long long)(y + 1) * (y + 1) + (long long)x * x;
       } else {
         const int d = x - (int)a;
@@ -132,7 +135,7 @@ __global__ void __launch_bounds__(EDT_ROW_THREADS)
       if (sq) sq[orow + x] = (int32_t)d2;
     }
     if (thr_bits) {
-      unsigned ball = __ballot_sync(0xffffffffu, x < W && d2 <= (long long)thr_sq);
+      unsigned ball = __ballot_sync(0xffffffffu, x < W && !nosite && d2 <= (long long)thr_sq);
       if ((tid & 31) == 0 && (x >> 5) < WW) thr_bits[(b * H + y) * (long long)WW + (x >> 5)] = ball;
     }
   }
@@ -155,7 +158,7 @@ int pcs_edt_bits(const uint32_t* bits, int invert, int B, int H, int W, double* 
   const int WW = pcs_words(W);
   uint16_t* g = (uint16_t*)ws;
   dim3 gc((W + 127) / 128, B);
-  k_edt_cols<<<gc, 128, 0, st>>>(bits, invert, g, H, W, WW);
+  PCS_LAUNCH("k_edt_cols", st, k_edt_cols<<<gc, 128, 0, st>>>(bits, invert, g, H, W, WW));
   int W2 = 1, L = 0;
   while (W2 <= W) {
     W2 <<= 1;
@@ -168,7 +171,7 @@ int pcs_edt_bits(const uint32_t* bits, int invert, int B, int H, int W, double* 
     smem_set = smem;
   }
   dim3 gr(H, B);
-  k_edt_rows<<<gr, EDT_ROW_THREADS, smem, st>>>(g, dist, sq, thr_bits, thr_sq, H, W, WW, W2, L);
+  PCS_LAUNCH("k_edt_rows", st, k_edt_rows<<<gr, EDT_ROW_THREADS, smem, st>>>(g, dist, sq, thr_bits, thr_sq, H, W, WW, W2, L));
   return pcs_check_launch("edt");
 }
 

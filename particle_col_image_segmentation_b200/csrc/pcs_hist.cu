@@ -220,14 +220,14 @@ int pcs_histogram_u16(const uint16_t* img, uint32_t* hist, int B, int H, int W, 
   cudaMemsetAsync(hist, 0, pcs_histogram_bytes(B), st);
   long long npix = (long long)H * W;
   dim3 grid((unsigned)((npix + HIST_PIX_PER_BLOCK - 1) / HIST_PIX_PER_BLOCK), B);
-  k_hist_u16<<<grid, HIST_THREADS, HIST_SMEM_BYTES, st>>>(img, hist, npix);
+  PCS_LAUNCH("k_hist_u16", st, k_hist_u16<<<grid, HIST_THREADS, HIST_SMEM_BYTES, st>>>(img, hist, npix));
   return pcs_check_launch("histogram");
 }
 
 int pcs_otsu_u16(const uint32_t* hist, int32_t* thr, int32_t* minmax, int B, int64_t npix, void* stream) {
   PCS_REQUIRE(B >= 1, "empty batch");
   PCS_REQUIRE(npix <= (1LL << 24), "Otsu parity needs at most 2^24 pixels per slice (float32 cumulative counts)");
-  k_otsu_u16<<<B, 1024, 0, (cudaStream_t)stream>>>(hist, thr, minmax);
+  PCS_LAUNCH("k_otsu_u16", (cudaStream_t)stream, k_otsu_u16<<<B, 1024, 0, (cudaStream_t)stream>>>(hist, thr, minmax));
   return pcs_check_launch("otsu");
 }
 

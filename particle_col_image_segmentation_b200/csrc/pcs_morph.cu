@@ -167,8 +167,8 @@ int pcs_dilate_bits(const uint32_t* in, uint32_t* out, const int32_t* runs, int 
   PCS_REQUIRE(n_runs >= 1 && runs != nullptr, "empty footprint");
   PCS_REQUIRE(in != out, "dilation cannot run in place");
   int WW = pcs_words(W);
-  k_dilate_bits<<<pcs_blocks((long long)B * H * WW, MORPH_THREADS), MORPH_THREADS, 0, (cudaStream_t)stream>>>(
-      in, out, (const PcsRun*)runs, n_runs, invert_in, border, invert_out, B, H, W, WW);
+  PCS_LAUNCH("k_dilate_bits", (cudaStream_t)stream, k_dilate_bits<<<pcs_blocks((long long)B * H * WW, MORPH_THREADS), MORPH_THREADS, 0, (cudaStream_t)stream>>>(
+      in, out, (const PcsRun*)runs, n_runs, invert_in, border, invert_out, B, H, W, WW));
   return pcs_check_launch("dilate");
 }
 
@@ -181,11 +181,11 @@ int pcs_majority_bits(const uint32_t* in, uint32_t* out, int size, int B, int H,
   unsigned g = pcs_blocks((long long)B * H * WW, MORPH_THREADS);
   cudaStream_t st = (cudaStream_t)stream;
   if (size == 3)
-    k_majority_bits<3><<<g, MORPH_THREADS, 0, st>>>(in, out, B, H, W, WW);
+    PCS_LAUNCH("k_majority_bits", st, k_majority_bits<3><<<g, MORPH_THREADS, 0, st>>>(in, out, B, H, W, WW));
   else if (size == 5)
-    k_majority_bits<5><<<g, MORPH_THREADS, 0, st>>>(in, out, B, H, W, WW);
+    PCS_LAUNCH("k_majority_bits", st, k_majority_bits<5><<<g, MORPH_THREADS, 0, st>>>(in, out, B, H, W, WW));
   else
-    k_majority_bits<7><<<g, MORPH_THREADS, 0, st>>>(in, out, B, H, W, WW);
+    PCS_LAUNCH("k_majority_bits", st, k_majority_bits<7><<<g, MORPH_THREADS, 0, st>>>(in, out, B, H, W, WW));
   return pcs_check_launch("majority");
 }
 
@@ -199,11 +199,11 @@ int pcs_median_u8(const uint8_t* img, uint8_t* out, int size, int B, int H, int 
   dim3 block(MED_TX, MED_TY);
   cudaStream_t st = (cudaStream_t)stream;
   if (size == 3)
-    k_median_u8<3><<<grid, block, 0, st>>>(img, out, H, W);
+    PCS_LAUNCH("k_median_u8", st, k_median_u8<3><<<grid, block, 0, st>>>(img, out, H, W));
   else if (size == 5)
-    k_median_u8<5><<<grid, block, 0, st>>>(img, out, H, W);
+    PCS_LAUNCH("k_median_u8", st, k_median_u8<5><<<grid, block, 0, st>>>(img, out, H, W));
   else
-    k_median_u8<7><<<grid, block, 0, st>>>(img, out, H, W);
+    PCS_LAUNCH("k_median_u8", st, k_median_u8<7><<<grid, block, 0, st>>>(img, out, H, W));
   return pcs_check_launch("median");
 }
 

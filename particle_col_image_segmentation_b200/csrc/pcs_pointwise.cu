@@ -274,8 +274,8 @@ static int launch_compare(const void* img, TT thr, const void* thr_dev, int cmp,
   PCS_REQUIRE(cmp >= 0 && cmp <= 5, "bad comparison code");
   PCS_REQUIRE(bits || mask, "no output requested");
   int WW = pcs_words(W);
-  k_compare<T, TT><<<pcs_blocks((long long)B * H * WW, PW_THREADS), PW_THREADS, 0, (cudaStream_t)stream>>>(
-      (const T*)img, thr, (const TT*)thr_dev, cmp, bits, mask, B, H, W, WW);
+  PCS_LAUNCH("k_compare", (cudaStream_t)stream, k_compare<T, TT><<<pcs_blocks((long long)B * H * WW, PW_THREADS), PW_THREADS, 0, (cudaStream_t)stream>>>(
+      (const T*)img, thr, (const TT*)thr_dev, cmp, bits, mask, B, H, W, WW));
   return pcs_check_launch("compare");
 }
 
@@ -307,8 +307,8 @@ int pcs_member_u8(const uint8_t* img, const uint8_t* member256, uint32_t* bits, 
   int rc = dims_ok(B, H, W);
   if (rc) return rc;
   int WW = pcs_words(W);
-  k_member_u8<<<pcs_blocks((long long)B * H * WW, PW_THREADS), PW_THREADS, 0, (cudaStream_t)stream>>>(img, member256, bits,
-                                                                                                     mask, B, H, W, WW);
+  PCS_LAUNCH("k_member_u8", (cudaStream_t)stream, k_member_u8<<<pcs_blocks((long long)B * H * WW, PW_THREADS), PW_THREADS, 0, (cudaStream_t)stream>>>(img, member256, bits,
+                                                                                                     mask, B, H, W, WW));
   return pcs_check_launch("member");
 }
 
@@ -316,7 +316,7 @@ int pcs_unpack_bits(const uint32_t* bits, uint8_t* mask, int B, int H, int W, vo
   int rc = dims_ok(B, H, W);
   if (rc) return rc;
   int WW = pcs_words(W);
-  k_unpack<<<pcs_blocks((long long)B * H * WW, PW_THREADS), PW_THREADS, 0, (cudaStream_t)stream>>>(bits, mask, B, H, W, WW);
+  PCS_LAUNCH("k_unpack", (cudaStream_t)stream, k_unpack<<<pcs_blocks((long long)B * H * WW, PW_THREADS), PW_THREADS, 0, (cudaStream_t)stream>>>(bits, mask, B, H, W, WW));
   return pcs_check_launch("unpack");
 }
 
@@ -326,8 +326,8 @@ int pcs_bits_logic(const uint32_t* a, const uint32_t* b, uint32_t* out, int op, 
   PCS_REQUIRE(op >= 0 && op <= 4, "bad logic op");
   PCS_REQUIRE(op == 4 || b != nullptr, "binary op needs two operands");
   int WW = pcs_words(W);
-  k_bits_logic<<<pcs_blocks((long long)B * H * WW, PW_THREADS), PW_THREADS, 0, (cudaStream_t)stream>>>(a, b, out, op, B, H,
-                                                                                                      W, WW);
+  PCS_LAUNCH("k_bits_logic", (cudaStream_t)stream, k_bits_logic<<<pcs_blocks((long long)B * H * WW, PW_THREADS), PW_THREADS, 0, (cudaStream_t)stream>>>(a, b, out, op, B, H,
+                                                                                                      W, WW));
   return pcs_check_launch("bits logic");
 }
 
@@ -337,13 +337,13 @@ int pcs_bits_count(const uint32_t* bits, uint64_t* counts, int B, int H, int W, 
   long long wps = (long long)H * pcs_words(W);
   cudaMemsetAsync(counts, 0, (size_t)B * 8, (cudaStream_t)stream);
   dim3 grid((unsigned)min((long long)64, (wps + PW_THREADS - 1) / PW_THREADS), B);
-  k_bits_count<<<grid, PW_THREADS, 0, (cudaStream_t)stream>>>(bits, (unsigned long long*)counts, wps);
+  PCS_LAUNCH("k_bits_count", (cudaStream_t)stream, k_bits_count<<<grid, PW_THREADS, 0, (cudaStream_t)stream>>>(bits, (unsigned long long*)counts, wps));
   return pcs_check_launch("bits count");
 }
 
 int pcs_lut_u8(uint8_t* img, const uint8_t* lut256, int64_t n, void* stream) {
   PCS_REQUIRE(n >= 1, "empty array");
-  k_lut_u8<<<pcs_blocks((n + 15) / 16, PW_THREADS), PW_THREADS, 0, (cudaStream_t)stream>>>(img, lut256, n);
+  PCS_LAUNCH("k_lut_u8", (cudaStream_t)stream, k_lut_u8<<<pcs_blocks((n + 15) / 16, PW_THREADS), PW_THREADS, 0, (cudaStream_t)stream>>>(img, lut256, n));
   return pcs_check_launch("lut");
 }
 
@@ -351,8 +351,8 @@ int pcs_assign_where_u8(uint8_t* img, const uint32_t* bits, int value, int B, in
   int rc = dims_ok(B, H, W);
   if (rc) return rc;
   int WW = pcs_words(W);
-  k_assign_where<<<pcs_blocks((long long)B * H * WW, PW_THREADS), PW_THREADS, 0, (cudaStream_t)stream>>>(img, bits,
-                                                                                                        (uint8_t)value, B, H, W, WW);
+  PCS_LAUNCH("k_assign_where", (cudaStream_t)stream, k_assign_where<<<pcs_blocks((long long)B * H * WW, PW_THREADS), PW_THREADS, 0, (cudaStream_t)stream>>>(img, bits,
+                                                                                                        (uint8_t)value, B, H, W, WW));
   return pcs_check_launch("assign where");
 }
 
@@ -369,11 +369,11 @@ int pcs_conn_planes(const void* img, int dtype, uint32_t* planes, uint32_t* high
   cudaStream_t st = (cudaStream_t)stream;
   int c8 = connectivity == 8;
   switch (dtype) {
-    case 0: k_conn_planes<uint8_t><<<g, PW_THREADS, 0, st>>>((const uint8_t*)img, planes, higher, all_fg, c8, B, H, W, WW); break;
-    case 1: k_conn_planes<uint16_t><<<g, PW_THREADS, 0, st>>>((const uint16_t*)img, planes, higher, all_fg, c8, B, H, W, WW); break;
-    case 2: k_conn_planes<int32_t><<<g, PW_THREADS, 0, st>>>((const int32_t*)img, planes, higher, all_fg, c8, B, H, W, WW); break;
-    case 3: k_conn_planes<float><<<g, PW_THREADS, 0, st>>>((const float*)img, planes, higher, all_fg, c8, B, H, W, WW); break;
-    case 4: k_conn_planes<double><<<g, PW_THREADS, 0, st>>>((const double*)img, planes, higher, all_fg, c8, B, H, W, WW); break;
+    case 0: PCS_LAUNCH("k_conn_planes", st, k_conn_planes<uint8_t><<<g, PW_THREADS, 0, st>>>((const uint8_t*)img, planes, higher, all_fg, c8, B, H, W, WW)); break;
+    case 1: PCS_LAUNCH("k_conn_planes", st, k_conn_planes<uint16_t><<<g, PW_THREADS, 0, st>>>((const uint16_t*)img, planes, higher, all_fg, c8, B, H, W, WW)); break;
+    case 2: PCS_LAUNCH("k_conn_planes", st, k_conn_planes<int32_t><<<g, PW_THREADS, 0, st>>>((const int32_t*)img, planes, higher, all_fg, c8, B, H, W, WW)); break;
+    case 3: PCS_LAUNCH("k_conn_planes", st, k_conn_planes<float><<<g, PW_THREADS, 0, st>>>((const float*)img, planes, higher, all_fg, c8, B, H, W, WW)); break;
+    case 4: PCS_LAUNCH("k_conn_planes", st, k_conn_planes<double><<<g, PW_THREADS, 0, st>>>((const double*)img, planes, higher, all_fg, c8, B, H, W, WW)); break;
     default: pcs_set_error("unsupported dtype for connectivity planes"); return PCS_ERR_UNSUPPORTED;
   }
   return pcs_check_launch("connectivity planes");
@@ -386,9 +386,9 @@ int pcs_gather(const void* img, int dtype, const int64_t* slice, const int64_t* 
   unsigned g = pcs_blocks(n, 256);
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
-    case 0: k_gather<uint8_t><<<g, 256, 0, st>>>((const uint8_t*)img, (const long long*)slice, (const long long*)idx, (long long*)out, n, slice_elems); break;
-    case 2: k_gather<int32_t><<<g, 256, 0, st>>>((const int32_t*)img, (const long long*)slice, (const long long*)idx, (long long*)out, n, slice_elems); break;
-    case 5: k_gather<long long><<<g, 256, 0, st>>>((const long long*)img, (const long long*)slice, (const long long*)idx, (long long*)out, n, slice_elems); break;
+    case 0: PCS_LAUNCH("k_gather", st, k_gather<uint8_t><<<g, 256, 0, st>>>((const uint8_t*)img, (const long long*)slice, (const long long*)idx, (long long*)out, n, slice_elems)); break;
+    case 2: PCS_LAUNCH("k_gather", st, k_gather<int32_t><<<g, 256, 0, st>>>((const int32_t*)img, (const long long*)slice, (const long long*)idx, (long long*)out, n, slice_elems)); break;
+    case 5: PCS_LAUNCH("k_gather", st, k_gather<long long><<<g, 256, 0, st>>>((const long long*)img, (const long long*)slice, (const long long*)idx, (long long*)out, n, slice_elems)); break;
     default: pcs_set_error("unsupported dtype for gather"); return PCS_ERR_UNSUPPORTED;
   }
   return pcs_check_launch("gather");

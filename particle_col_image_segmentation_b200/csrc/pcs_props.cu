@@ -246,7 +246,7 @@ extern "C" {
 
 int pcs_table_init(int64_t* table, int64_t cap, void* stream) {
   PCS_REQUIRE(cap >= 1 && table != nullptr, "empty table");
-  k_table_init<<<pcs_blocks(cap, 256), 256, 0, (cudaStream_t)stream>>>((long long*)table, cap);
+  PCS_LAUNCH("k_table_init", (cudaStream_t)stream, k_table_init<<<pcs_blocks(cap, 256), 256, 0, (cudaStream_t)stream>>>((long long*)table, cap));
   return pcs_check_launch("table init");
 }
 
@@ -264,7 +264,7 @@ int pcs_region_table(const void* labels, int label_bytes, const void* intensity,
   long long* tb = (long long*)table;
   if (intensity == nullptr) intensity_dtype = -1;
 #define LAUNCH(LT, IT) \
-  k_region_table<LT, IT><<<g, PROPS_THREADS, 0, st>>>((const LT*)labels, (const IT*)intensity, fg_bits, ov_bits, offsets, tb, cap, B, H, W, WW, strips)
+  PCS_LAUNCH("k_region_table", st, (k_region_table<LT, IT><<<g, PROPS_THREADS, 0, st>>>((const LT*)labels, (const IT*)intensity, fg_bits, ov_bits, offsets, tb, cap, B, H, W, WW, strips)))
   if (label_bytes == 4) {
     if (intensity_dtype == 1)
       LAUNCH(int32_t, uint16_t);
@@ -295,9 +295,9 @@ int pcs_select_labels(const void* labels, int label_bytes, const uint8_t* keep, 
   const int WW = pcs_words(W);
   unsigned g = pcs_blocks((long long)B * H * WW, 256);
   if (label_bytes == 4)
-    k_select_labels<int32_t><<<g, 256, 0, (cudaStream_t)stream>>>((const int32_t*)labels, keep, lut_stride, out, B, H, W, WW);
+    PCS_LAUNCH("k_select_labels", (cudaStream_t)stream, k_select_labels<int32_t><<<g, 256, 0, (cudaStream_t)stream>>>((const int32_t*)labels, keep, lut_stride, out, B, H, W, WW));
   else
-    k_select_labels<long long><<<g, 256, 0, (cudaStream_t)stream>>>((const long long*)labels, keep, lut_stride, out, B, H, W, WW);
+    PCS_LAUNCH("k_select_labels", (cudaStream_t)stream, k_select_labels<long long><<<g, 256, 0, (cudaStream_t)stream>>>((const long long*)labels, keep, lut_stride, out, B, H, W, WW));
   return pcs_check_launch("select labels");
 }
 
@@ -306,8 +306,8 @@ int pcs_select_by_area(const int32_t* labels, const uint32_t* fg_bits, const int
   PCS_REQUIRE(B >= 1 && H >= 1 && W >= 1, "empty batch or image");
   PCS_REQUIRE(labels && fg_bits && table && offsets && out, "null argument");
   const int WW = pcs_words(W);
-  k_select_by_area<<<pcs_blocks((long long)B * H * WW, 256), 256, 0, (cudaStream_t)stream>>>(
-      labels, fg_bits, (const long long*)table, cap, offsets, min_size, out, B, H, W, WW);
+  PCS_LAUNCH("k_select_by_area", (cudaStream_t)stream, k_select_by_area<<<pcs_blocks((long long)B * H * WW, 256), 256, 0, (cudaStream_t)stream>>>(
+      labels, fg_bits, (const long long*)table, cap, offsets, min_size, out, B, H, W, WW));
   return pcs_check_launch("select by area");
 }
 
@@ -316,13 +316,13 @@ int pcs_roi_sums_f64(const int32_t* labels, const double* planes, int K, int64_t
   cudaStream_t st = (cudaStream_t)stream;
   if (n_rois == 0) return PCS_OK;
   cudaMemsetAsync(out, 0, (size_t)n_rois * K * 8, st);
-  k_roi_sums<<<pcs_blocks(npix, 256), 256, 0, st>>>(labels, planes, K, npix, n_rois, out);
+  PCS_LAUNCH("k_roi_sums", st, k_roi_sums<<<pcs_blocks(npix, 256), 256, 0, st>>>(labels, planes, K, npix, n_rois, out));
   return pcs_check_launch("roi sums");
 }
 
 int pcs_min_dist_f64(const double* a, int64_t na, const double* b, int64_t nb, double* out, void* stream) {
   if (na <= 0) return PCS_OK;
-  k_min_dist<<<pcs_blocks(na, 128), 128, 0, (cudaStream_t)stream>>>(a, na, b, nb, out);
+  PCS_LAUNCH("k_min_dist", (cudaStream_t)stream, k_min_dist<<<pcs_blocks(na, 128), 128, 0, (cudaStream_t)stream>>>(a, na, b, nb, out));
   return pcs_check_launch("min dist");
 }
 

@@ -47,6 +47,9 @@ def label(label_image, background=None, return_num=False, connectivity=None):
     return (out, int(counts[0].item())) if return_num else out
 
 
+_HOST_CACHE = {}
+
+
 class RegionProperties:
     """Table-backed stand-in for ``skimage.measure._regionprops.RegionProperties``."""
 
@@ -87,7 +90,12 @@ class RegionProperties:
 
     def _host_labels(self):
         li = self._label_image
-        return li.cpu().numpy() if isinstance(li, torch.Tensor) else np.asarray(li)
+        if isinstance(li, torch.Tensor):  # device labels: fetch once, share between regions
+            key = (li.data_ptr(), tuple(li.shape))
+            if _HOST_CACHE.get("key") != key:
+                _HOST_CACHE["key"], _HOST_CACHE["arr"] = key, li.cpu().numpy()
+            return _HOST_CACHE["arr"]
+        return np.asarray(li)
 
     @property
     def image(self):

@@ -1,0 +1,45 @@
+"""Device-backed ``refine_boundaries.py`` as a function.
+
+The reference file is top-level script code bound to a hard-coded HDF5 path
+(refine_boundaries.py:28-31); its pixel work (:44-64) is: threshold the ilastik
+boundary-probability map, EDT of the foreground, plateau local maxima of the
+distance, label the maxima as watershed markers.  The watershed call itself (:73)
+sits in code the author marks as not working (:54) and is a SURVEY 8(f) "next" row.
+"""
+
+import numpy as np
+import torch
+
+from . import _io, ops
+
+
+def refine_boundaries(boundary_map, threshold=0.5):
+    """-> dict(binary_mask bool, distance float64, local_max bool, markers int32).
+
+    ``binary_mask = boundary_map < threshold``            refine_boundaries.py:44-45
+    ``distance = distance_transform_edt(binary_mask)``    refine_boundaries.py:60
+    ``local_max = local_maxima(distance)``                refine_boundaries.py:63
+    ``markers = label(local_max)``                        refine_boundaries.py:64
+
+    Maxima are found on the exact integer squared distance: sqrt is strictly
+    monotone, so plateaus and strict inequalities are the same as on ``distance``.
+    """
+    np_in = _io.is_numpy(boundary_map)
+    t = _io.image_2d(boundary_map)
+    if t.dtype not in (torch.float32, torch.float64):
+        t = t.to(torch.float64)
+    H, W = int(t.shape[1]), int(t.shape[2])
+    bits = ops.compare(t, "<", float(threshold))[0]
+    dist, sq, _ = ops.edt(bits, W, want_dist=True, want_sq=True)
+    if H < 3 or W < 3:
+        maxima = torch.zeros_like(bits)
+    else:
+        maxima = ops.local_maxima(sq, connectivity=8)
+    markers, counts, _ = ops.label_bits(maxima, W, connectivity=8, dtype=torch.int32)
+    out = {
+        "binary_mask": _io.bits_to_bool(bits, W, np_in),
+        "distance": _io.back(dist[0], np_in),
+        "local_max": _io.bits_to_bool(maxima, W, np_in),
+        "markers": _io.back(markers[0], np_in),
+    }
+    return out

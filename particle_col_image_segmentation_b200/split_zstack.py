@@ -93,7 +93,7 @@ class SegmentResult:
         }
 
 
-def segment_zstack_device(stack, denoise_size=5, min_size=20, chunk=16, max_regions_per_slice=1 << 16, out=None, z0=0):
+def segment_zstack_device(stack, denoise_size=5, min_size=20, chunk=16, max_regions_per_slice=1 << 14, out=None, z0=0):
     """Full pipeline over a device-resident ``(Z, H, W)`` uint16 stack.
 
     Asynchronous on the current stream; no host synchronisation inside.  ``out`` may
@@ -158,7 +158,7 @@ def segment_zstack_device(stack, denoise_size=5, min_size=20, chunk=16, max_regi
     return out
 
 
-def segment_zstack(stack, denoise_size=5, min_size=20, chunk=16, max_regions_per_slice=1 << 16, z0=0):
+def segment_zstack(stack, denoise_size=5, min_size=20, chunk=16, max_regions_per_slice=1 << 14, z0=0):
     """numpy ``(Z, H, W)`` (or a single ``(H, W)`` slice) in, dict of numpy arrays out:
     ``threshold, mask, labels, refined, edt, table, counts`` -- the same keys and dtypes
     as ``oracle.pipeline.segment_zstack``."""
@@ -174,3 +174,41 @@ def segment_zstack(stack, denoise_size=5, min_size=20, chunk=16, max_regions_per
     if single:
         d = {k: (v[0] if k not in ("table",) else v) for k, v in d.items()}
     return d
+
+
+# ---------------------------------------------------------------- host-buffer (end-to-end) path
+_E2E_CACHE = {}
+
+
+def alloc_host_outputs(Z, H, W):
+    """Pinned host buffers for every pipeline output of a ``(Z, H, W)`` stack."""
+    return {
+        "mask": torch.empty((Z, H, W), dtype=torch.uint8).pin_memory(),
+        "labels": torch.empty((Z, H, W), dtype=torch.int32).pin_memory(),
+        "refined": torch.empty((Z, H, W), dtype=torch.uint8).pin_memory(),
+        "edt": torch.empty((Z, H, W), dtype=torch.float64).pin_memory(),
+        "threshold": torch.empty(Z, dtype=torch.int32).pin_memory(),
+        "counts": torch.empty(Z, dtype=torch.int32).pin_memory(),
+    }
+
+
+def segment_zstack_pinned(host_in, host_out, denoise_size=5, min_size=20, chunk=16, max_regions_per_slice=1 << 14):
+    """Host buffers in, host buffers out: H2D copy of the stack, the device pipeline, D2H copy
+    of all five outputs and the table.  Device buffers are cached between calls.
+    Returns the number of table rows (``host_out['table']`` holds them)."""
+    dev = _io.device()
+    key = (str(dev), tuple(host_in.shape))
+    st = _E2E_CACHE.get(key)
+    if st is None:
+        st = {"in": torch.empty(tuple(host_in.shape), dtype=torch.uint16, device=dev), "res": None}
+        _E2E_CACHE.clear()
+        _E2E_CACHE[key] = st
+    st["in"].copy_(host_in, non_blocking=True)
+    res = segment_zstack_device(st["in"], denoise_size, min_size, chunk, max_regions_per_slice, out=st["res"])
+    st["res"] = res
+    for k in ("mask", "labels", "refined", "edt", "threshold", "counts"):
+        host_out[k].copy_(getattr(res, k), non_blocking=True)
+    table = res.table_device()
+    host_out["table"] = table.cpu()
+    torch.cuda.synchronize()
+    return int(table.shape[0])

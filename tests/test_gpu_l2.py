@@ -1,0 +1,139 @@
+"""The device-backed mirrors of the reference's L2 functions against (a) the outputs
+of the reference's own functions frozen in tests/golden and (b) the oracle on fresh
+seeded inputs.  Areas, centroids, bboxes, counts and images are bit-exact."""
+
+import numpy as np
+import pytest
+import torch
+from scipy import ndimage as ndi
+
+from oracle import l2 as ol2
+from oracle import nanosims as onano
+from oracle import refine as orefine
+from particle_col_image_segmentation_b200 import synth
+
+from helpers import assert_summary_equal
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ta():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from particle_col_image_segmentation_b200 import tiff_analysis
+
+    return tiff_analysis
+
+
+def test_single_file_path_matches_reference_golden(ta, golden):
+    arrays, meta = golden
+    types = {1: "3D05", 2: "Particle", 3: "Background"}
+    den = ta.median_filter(arrays["A_raw"], size=ta.DENOISE_SIZE)
+    assert np.array_equal(den, arrays["A_denoised"])
+    res = ta.get_cell_positions_and_areas(den, types, merged=True)
+    assert_summary_equal(ol2.summarize_positions(res), meta["A_positions"])
+    cnt, dens, ratio = ta.get_cell_counts_and_densities(res[0], res[1], res[2])
+    assert {k: int(v) for k, v in cnt.items()} == meta["A_counts"]["count"]
+    assert dens == meta["A_counts"]["density"] and ratio == meta["A_counts"]["ratio"]
+    rec, area = ta.recreate_particle_area(den, types, res[2])
+    assert np.array_equal(rec, arrays["A_recreated"]) and float(area) == meta["A_particle_area"]
+    _, images = ta.get_cell_clusters_from_distances(den, res[0], res[1], types)
+    for k, im in images.items():
+        assert im.dtype == bool and np.array_equal(im, arrays[f"A_merged_image_{k}"]), k
+    out = ta.process_single_array(arrays["A_raw"][None], types)
+    assert np.array_equal(out["recreated"], arrays["A_recreated"]) and float(out["particle_area"]) == meta["A_particle_area"]
+
+
+def test_multiclass_matches_reference_golden(ta, golden):
+    arrays, meta = golden
+    res = ta.get_cell_positions_and_areas(arrays["B_image"], ta.BASE_TYPE_MAP, merged=True)
+    assert_summary_equal(ol2.summarize_positions(res), meta["B_positions"])
+    rec, area = ta.recreate_particle_area(arrays["B_image"], ta.BASE_TYPE_MAP, res[2])
+    assert np.array_equal(rec, arrays["B_recreated"]) and float(area) == meta["B_particle_area"]
+
+
+def test_channel_ops_match_reference_golden(ta, golden):
+    arrays, meta = golden
+    dapi, rfp = arrays["C_dapi"], arrays["C_rfp"]
+    assert np.array_equal(ta.combine_cell_positions_and_clusters(dapi, rfp), arrays["C_dapi_updated"])
+    base = ta.get_rfp_base_arr(rfp.copy(), ["3D05", "6B07"])
+    assert np.array_equal(base, arrays["C_rfp_base"])
+    comb = ta.combine_channels(base.copy(), {"RFP": rfp, "DAPI": dapi}, ["3D05", "6B07"])
+    assert np.array_equal(comb, arrays["C_combined"])
+    assert np.array_equal(ta.relabel_other_channel(rfp, "RFP"), arrays["C_other_updated"])
+    up, n = ta.fill_particle_area(dapi, 2, 1, 2)
+    assert np.array_equal(up, arrays["C_fill"]) and int(n) == meta["C_fill_count"]
+
+
+@pytest.mark.parametrize("seed,size", [(21, 256), (22, 300), (23, 512)])
+def test_l2_matches_oracle_fresh_inputs(ta, seed, size):
+    raw = synth.class_image(size, size + 37, seed=seed, noise=0.03)
+    den = ta.median_filter(raw, size=5)
+    assert np.array_equal(den, ndi.median_filter(raw, size=5))
+    types = {1: "C3M10", 2: "Particle", 3: "Background"}
+    got = ta.get_cell_positions_and_areas(den, types, merged=True)
+    want = ol2.get_cell_positions_and_areas(den, types, merged=True)
+    assert_summary_equal(ol2.summarize_positions(got), ol2.summarize_positions(want))
+    g, ng = ta.recreate_particle_area(den, types, got[2])
+    w, nw = ol2.recreate_particle_area(den, types, want[2])
+    assert np.array_equal(g, w) and ng == nw
+    other = synth.class_image(size, size + 37, seed=seed + 50, noise=0.0)
+    assert np.array_equal(ta.combine_cell_positions_and_clusters(den, other), ol2.combine_cell_positions_and_clusters(den, other))
+    # get_merged_regions at the public boundary (numpy mask + region list)
+    regs = got[0].get("C3M10", []) + got[1].get("C3M10", [])
+    mg, img = ta.get_merged_regions(den == 1, regs)
+    oregs = want[0].get("C3M10", []) + want[1].get("C3M10", [])
+    mo, imo = ol2.get_merged_regions(den == 1, oregs)
+    assert np.array_equal(img, imo) and len(mg) == len(mo)
+    for a, b in zip(mg, mo):
+        assert a["area"] == b["area"] and a["bbox"] == b["bbox"] and np.array_equal(a["centroid"], b["centroid"])
+
+
+def test_fill_particle_area_edge_cases(ta):
+    img = np.full((40, 50), 3, np.uint8)  # no particle at all: scipy's EDT quirk decides
+    img[0:3, 0:4] = 1
+    img[20:25, 20:25] = 1
+    g, ng = ta.fill_particle_area(img, 2, 1, 2)
+    w, nw = ol2.fill_particle_area(img, 2, 1, 2)
+    assert np.array_equal(g, w) and ng == nw
+    img[10:12, 30:33] = 2
+    g, ng = ta.fill_particle_area(img, 2, 1, 2)
+    w, nw = ol2.fill_particle_area(img, 2, 1, 2)
+    assert np.array_equal(g, w) and ng == nw
+
+
+def test_normalize_ds_arr(ta):
+    a = np.zeros((8, 9), np.uint8)
+    assert ta.normalize_ds_arr(a[None]).shape == (8, 9) and ta.normalize_ds_arr(a[..., None]).shape == (8, 9)
+    assert ta.normalize_ds_arr(a) is a
+    with pytest.raises(ValueError):
+        ta.normalize_ds_arr(np.zeros((2, 3, 4)))
+
+
+@pytest.mark.parametrize("size", [160, 400])
+def test_refine_boundaries(ta, size):
+    from particle_col_image_segmentation_b200 import refine_boundaries as rb
+
+    _, prob = synth.touching_particles(size, size + 11, seed=size)
+    got = rb.refine_boundaries(prob)
+    want = orefine.refine_boundaries(prob)
+    for k in ("binary_mask", "distance", "local_max", "markers"):
+        assert got[k].dtype == want[k].dtype, k
+        assert np.array_equal(got[k], want[k]), k
+
+
+@pytest.mark.parametrize("k", [5, 7])
+def test_nanosims(ta, k):
+    from particle_col_image_segmentation_b200 import nanosims
+
+    planes, roi, set_id, agg = synth.nanosims_stack(256, k, 120, seed=1004)
+    red = np.isin(roi, np.nonzero(set_id == 1)[0] + 1)
+    green = np.isin(roi, np.nonzero(set_id == 2)[0] + 1)
+    got = nanosims.analyse(planes, red, green, agg)
+    want = onano.analyse(planes, red, green, agg)
+    assert got.shape == want.shape
+    assert np.array_equal(got, want), np.argwhere(got != want)[:5]
+    c, t, m = nanosims.activity_vs_distance(got[:, 2 + k], got[:, -1], np.linspace(0, 5, 11))
+    c2, t2, m2 = onano.activity_vs_distance(want[:, 2 + k], want[:, -1], np.linspace(0, 5, 11))
+    assert np.array_equal(c, c2) and np.array_equal(t, t2)
