@@ -43,8 +43,10 @@ KERNEL_BYTES_PER_VOXEL = {
     "k_ccl_select": 0.25,
     "k_region_table": 4.0 + 2.0,
     "k_select_by_area": 0.25,
-    "k_edt_cols": 2.0 + 0.125,
-    "k_edt_rows": 8.0 + 2.0,
+    "k_edt_transpose": 0.25,
+    "k_edt_carry": 0.25,
+    "k_edt_near": 8.0 + 0.25,
+    "k_edt_far": 8.0 + 0.25,
 }
 
 

@@ -11,71 +11,92 @@
 // scipy computes an int32 feature transform and then sqrt(float64(dy^2+dx^2)); an
 // exact integer squared distance followed by IEEE sqrt is therefore bit-identical.
 //
-// Pass 1 (columns): g(y,x) = distance to the nearest background pixel in column x.
-// Pass 2 (rows): D2(y,x) = min_c (x-c)^2 + g(y,c)^2.  The arg-min is monotone in x
-// (the cost matrix is totally monotone), so the row is solved by divide and
-// conquer: the middle column first, then each half with the candidate range cut
-// at the parent's arg-min -- O(W log W) integer evaluations per row, no divisions,
-// no stacks, level-synchronous inside one CTA with shuffle reductions.  The
-// column distance also bounds the search window (|x-c| < g(y,x)), which makes
-// rows through small particles nearly free.
+// Column pass without a column image.  The mask is transposed 32x32 bits at a time
+// into VERTICAL words (k_edt_transpose: bit j of vw[band][x] is row 32*band + j of
+// column x) and a 64-step scan per column records, for every band, the distance to
+// the nearest background row above / below the band (k_edt_carry).  The vertical
+// distance g(y, x) of any pixel is then two bit scans (clz / ffs) of one word plus a
+// carry -- 0.25 B/pixel of traffic instead of a 2 B/pixel distance image written,
+// re-read and rewritten.
+//
+// Row pass: D2(y, x) = min_c (x-c)^2 + g(y, c)^2.
+//   * k_edt_near (CTA per 32-row band x 256-column tile): a pixel with g <= EDT_DMAX only
+//     needs candidates with |x-c| < g, so an outward search c = x -+ d that stops as soon
+//     as d^2 >= best is exact, stays inside the tile + 40-pixel halo held in shared memory
+//     and costs O(distance) per foreground pixel; pixels with a larger g flag their row;
+//   * k_edt_far (warp per flagged row): the arg-min is monotone in x (the cost matrix is totally
+//     monotone), so the row is solved by divide and conquer -- the middle column first,
+//     then each half with the candidate range cut at the parent's arg-min: O(W log W)
+//     integer evaluations, no divisions, no stacks, shuffle reductions inside the warp.
 #include "pcs_common.cuh"
 
 #include "pcs.h"
 
 #define EDT_INF 0xFFFFu
-#define EDT_ROW_THREADS 256
+#define EDT_DMAX 40u
 #define EDT_KEY_MAX 0xFFFFFFFFFFFFFFFFull
+#define EDT_WARPS 8
 
-// thread per column
-__global__ void __launch_bounds__(128)
-    k_edt_cols(const uint32_t* __restrict__ bits, int invert, uint16_t* __restrict__ g, int H, int W, int WW) {
-  int x = blockIdx.x * blockDim.x + threadIdx.x;
-  if (x >= W) return;
-  long long b = blockIdx.y;
-  const uint32_t* col = bits + b * (long long)H * WW + (x >> 5);
-  uint16_t* gc = g + b * (long long)H * W + x;
-  const int sh = x & 31;
-  const uint32_t flip = invert ? 1u : 0u;
-  uint32_t d = EDT_INF;
-#pragma unroll 8
-  for (int y = 0; y < H; ++y) {
-    uint32_t fg = ((__ldg(col + (long long)y * WW) >> sh) & 1u) ^ flip;
-    d = fg ? (d == EDT_INF ? EDT_INF : d + 1u) : 0u;
-    gc[(long long)y * W] = (uint16_t)d;
+// warp per (slice, band, word): 32 rows x 32 columns of bits -> 32 vertical words
+__global__ void __launch_bounds__(256)
+    k_edt_transpose(const uint32_t* __restrict__ bits, int invert, uint32_t* __restrict__ vw, int B, int H, int W, int WW,
+                    int NB) {
+  long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  long long total = (long long)B * NB * WW;
+  if (g >= total) return;
+  const int k = (int)(g % WW);
+  const int q = (int)((g / WW) % NB);
+  const long long b = g / ((long long)WW * NB);
+  const int y = (q << 5) + lane;
+  uint32_t w = 0xffffffffu;  // rows past the image never act as background
+  if (y < H) {
+    w = bits[(b * H + y) * (long long)WW + k];
+    if (invert) w = ~w;
   }
-  d = EDT_INF;
-#pragma unroll 8
-  for (int y = H - 1; y >= 0; --y) {
-    uint32_t fg = ((__ldg(col + (long long)y * WW) >> sh) & 1u) ^ flip;
-    d = fg ? (d == EDT_INF ? EDT_INF : d + 1u) : 0u;
-    uint32_t up = gc[(long long)y * W];
-    gc[(long long)y * W] = (uint16_t)min(up, d);
+  uint32_t mine = 0;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    uint32_t v = __ballot_sync(0xffffffffu, (w >> i) & 1u);
+    if (lane == i) mine = v;
+  }
+  vw[(b * NB + q) * (long long)(WW << 5) + (k << 5) + lane] = mine;
+}
+
+// thread per column: distance from the band edge to the nearest background row beyond it
+__global__ void __launch_bounds__(128)
+    k_edt_carry(const uint32_t* __restrict__ vw, uint16_t* __restrict__ up, uint16_t* __restrict__ dn, int W, int Wp, int NB) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= W) return;
+  const long long b = blockIdx.y;
+  const uint32_t* v = vw + b * (long long)NB * Wp + x;
+  uint16_t* u = up + b * (long long)NB * Wp + x;
+  uint16_t* d = dn + b * (long long)NB * Wp + x;
+  uint32_t carry = EDT_INF;
+#pragma unroll 4
+  for (int q = 0; q < NB; ++q) {
+    u[(long long)q * Wp] = (uint16_t)carry;  // from row 32q - 1 upwards
+    const uint32_t z = ~__ldg(v + (long long)q * Wp);
+    carry = z ? (uint32_t)__clz(z) : (carry == EDT_INF ? EDT_INF : carry + 32u);  // 31 - msb
+  }
+  carry = EDT_INF;
+#pragma unroll 4
+  for (int q = NB - 1; q >= 0; --q) {
+    d[(long long)q * Wp] = (uint16_t)carry;  // from row 32(q+1) downwards
+    const uint32_t z = ~__ldg(v + (long long)q * Wp);
+    carry = z ? (uint32_t)(__ffs(z) - 1) : (carry == EDT_INF ? EDT_INF : carry + 32u);
   }
 }
 
-// CTA per row
-__global__ void __launch_bounds__(EDT_ROW_THREADS)
-    k_edt_rows(const uint16_t* __restrict__ g, double* __restrict__ dist, int32_t* __restrict__ sq,
-               uint32_t* __restrict__ thr_bits, int thr_sq, int H, int W, int WW, int W2, int L) {
-  extern __shared__ uint16_t smem[];
-  uint16_t* gs = smem;      // column distances of this row
-  uint16_t* am = smem + W;  // arg-min column per x
-  const int tid = threadIdx.x;
-  const int y = blockIdx.x;
-  const long long b = blockIdx.y;
-  const uint16_t* grow = g + (b * H + y) * (long long)W;
-  for (int x = tid; x < W; x += EDT_ROW_THREADS) gs[x] = grow[x];
-  __syncthreads();
-
+// divide-and-conquer row solve by one warp; gs = column distances, am = arg-min per x
+__device__ __forceinline__ void edt_row_dc(const uint16_t* gs, uint16_t* am, int W, int W2, int L, int lane) {
   for (int l = 0; l < L; ++l) {
     const int step = W2 >> (l + 1);
     const int nodes = 1 << l;
-    int gsz = EDT_ROW_THREADS >> l;
-    gsz = gsz > 32 ? 32 : (gsz < 1 ? 1 : gsz);
-    const int groups = EDT_ROW_THREADS / gsz;
-    const int sub = tid & (gsz - 1);
-    for (int j = tid / gsz; j < nodes; j += groups) {
+    const int gsz = l < 5 ? (32 >> l) : 1;
+    const int groups = 32 / gsz;
+    const int sub = lane & (gsz - 1);
+    for (int j = lane / gsz; j < nodes; j += groups) {
       const int xp = step * (2 * j + 1);  // 1-based position
       const bool valid = xp <= W;
       const int x = xp - 1;
@@ -110,68 +131,187 @@ __global__ void __launch_bounds__(EDT_ROW_THREADS)
       }
       if (valid && sub == 0) am[x] = key == EDT_KEY_MAX ? (uint16_t)EDT_INF : (uint16_t)(key & 0xffffu);
     }
-    __syncthreads();
+    __syncwarp();
   }
+}
 
-  const long long orow = (b * H + y) * (long long)W;
+// vertical distance of row r of a band from the column word z (zero bits = background rows)
+__device__ __forceinline__ uint32_t edt_vdist(uint32_t z, int r, uint32_t cu, uint32_t cd) {
+  if ((z >> r) & 1u) return 0u;
+  const uint32_t zu = z & (0xffffffffu >> (31 - r));  // background rows at or above r
+  const uint32_t gu = zu ? (uint32_t)(r - (31 - __clz(zu))) : (cu == EDT_INF ? EDT_INF : cu + (uint32_t)r + 1u);
+  const uint32_t zd = z >> r;  // background rows at or below r
+  const uint32_t gd = zd ? (uint32_t)(__ffs(zd) - 1) : (cd == EDT_INF ? EDT_INF : cd + 32u - (uint32_t)r);
+  return min(gu, gd);
+}
+
+// Phase 1: CTA per (column tile, band, slice).  Every pixel whose vertical distance is at most
+// EDT_DMAX is final after an outward search inside the tile + halo; the others flag their row.
+#define EDT_TW 256
+#define EDT_HALO 40
+#define EDT_TWH (EDT_TW + 2 * EDT_HALO)
+__global__ void __launch_bounds__(EDT_TW)
+    k_edt_near(const uint32_t* __restrict__ vw, const uint16_t* __restrict__ up, const uint16_t* __restrict__ dn,
+               double* __restrict__ dist, int32_t* __restrict__ sq, uint32_t* __restrict__ thr_bits, int thr_sq,
+               uint8_t* __restrict__ row_far, int H, int W, int WW, int NB) {
+  __shared__ uint16_t g[32][EDT_TWH];
+  const int tid = threadIdx.x;
   const int Wp = WW << 5;
-  for (int x0 = 0; x0 < Wp; x0 += EDT_ROW_THREADS) {
-    const int x = x0 + tid;
+  const int x0 = blockIdx.x * EDT_TW;
+  const int q = blockIdx.y;
+  const long long b = blockIdx.z;
+  const long long band = (b * NB + q) * (long long)Wp;
+  for (int col = tid; col < EDT_TWH; col += EDT_TW) {
+    const int x = x0 - EDT_HALO + col;
+    if (x >= 0 && x < W) {
+      const uint32_t z = ~__ldg(vw + band + x);
+      const uint32_t cu = __ldg(up + band + x), cd = __ldg(dn + band + x);
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) g[r][col] = (uint16_t)edt_vdist(z, r, cu, cd);
+    } else {
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) g[r][col] = (uint16_t)EDT_INF;  // outside the image: no site
+    }
+  }
+  __syncthreads();
+  const int x = x0 + tid;
+  const int col = tid + EDT_HALO;
+  const int rows = min(32, H - (q << 5));
+  for (int r = 0; r < rows; ++r) {
+    const int y = (q << 5) + r;
+    uint32_t d2 = 0;
+    bool far = false;
+    if (x < W) {
+      const uint32_t gx = g[r][col];
+      if (gx > EDT_DMAX) {
+        far = true;
+      } else if (gx != 0u) {
+        uint32_t best = gx * gx;
+        for (uint32_t dd = 1; dd * dd < best; ++dd) {  // dd < gx <= EDT_HALO: stays inside the tile + halo
+          const uint32_t d2d = dd * dd;
+          const uint32_t g1 = g[r][col - (int)dd], g2 = g[r][col + (int)dd];
+          if (g1 != EDT_INF) best = min(best, d2d + g1 * g1);
+          if (g2 != EDT_INF) best = min(best, d2d + g2 * g2);
+        }
+        d2 = best;
+      }
+      if (!far) {
+        const long long o = (b * H + y) * (long long)W + x;
+        if (dist) dist[o] = d2 ? sqrt((double)d2) : 0.0;
+        if (sq) sq[o] = (int32_t)d2;
+      }
+    }
+    if (__any_sync(0xffffffffu, far) && (tid & 31) == 0) row_far[b * H + y] = 1;
+    if (thr_bits) {
+      unsigned ball = __ballot_sync(0xffffffffu, x < W && !far && d2 <= (uint32_t)thr_sq);
+      if ((tid & 31) == 0 && (x >> 5) < WW) thr_bits[(b * H + y) * (long long)WW + (x >> 5)] = ball;
+    }
+  }
+}
+
+// Phase 2: warp per flagged row -- full divide-and-conquer solve, rewrites the whole row
+__global__ void __launch_bounds__(EDT_WARPS * 32)
+    k_edt_far(const uint32_t* __restrict__ vw, const uint16_t* __restrict__ up, const uint16_t* __restrict__ dn,
+              double* __restrict__ dist, int32_t* __restrict__ sq, uint32_t* __restrict__ thr_bits, int thr_sq,
+              const uint8_t* __restrict__ row_far, int H, int W, int WW, int NB, int W2, int L) {
+  extern __shared__ uint16_t smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int Wp = WW << 5;
+  const int y = blockIdx.x * nwarps + warp;
+  const long long b = blockIdx.y;
+  if (y >= H || !row_far[b * H + y]) return;
+  uint16_t* gs = smem + (size_t)warp * 2 * Wp;
+  uint16_t* am = gs + Wp;
+  const int q = y >> 5, r = y & 31;
+  const long long band = (b * NB + q) * (long long)Wp;
+  for (int x = lane; x < Wp; x += 32) {
+    uint32_t gv = 0;
+    if (x < W) gv = edt_vdist(~__ldg(vw + band + x), r, __ldg(up + band + x), __ldg(dn + band + x));
+    gs[x] = (uint16_t)gv;
+  }
+  __syncwarp();
+  edt_row_dc(gs, am, W, W2, L, lane);
+  const long long orow = (b * H + y) * (long long)W;
+  for (int x = lane; x < Wp; x += 32) {
     long long d2 = 0;
     bool nosite = false;
     if (x < W) {
-      const uint32_t a = am[x];
-      if (a == EDT_INF) {
-        // no background pixel anywhere: scipy measures to the virtual point (-1, 0);
-        // for the threshold output (dilation of an empty mask) the distance is infinite
-        nosite = true;
-        d2 = (long long)(y + 1) * (y + 1) + (long long)x * x;
-      } else {
-        const int d = x - (int)a;
-        const uint32_t gv = gs[a];
-        d2 = (long long)d * d + (long long)gv * gv;
+      const uint32_t gx = gs[x];
+      if (gx != 0u) {
+        const uint32_t a = am[x];
+        if (a == EDT_INF) {
+          // no background pixel anywhere: scipy measures to the virtual point (-1, 0);
+          // for the threshold output (dilation of an empty mask) the distance is infinite
+          nosite = true;
+          d2 = (long long)(y + 1) * (y + 1) + (long long)x * x;
+        } else {
+          const int dd = x - (int)a;
+          const uint32_t gv = gs[a];
+          d2 = (long long)dd * dd + (long long)gv * gv;
+        }
       }
       if (dist) dist[orow + x] = sqrt((double)d2);
       if (sq) sq[orow + x] = (int32_t)d2;
     }
     if (thr_bits) {
       unsigned ball = __ballot_sync(0xffffffffu, x < W && !nosite && d2 <= (long long)thr_sq);
-      if ((tid & 31) == 0 && (x >> 5) < WW) thr_bits[(b * H + y) * (long long)WW + (x >> 5)] = ball;
+      if (lane == 0) thr_bits[(b * H + y) * (long long)WW + (x >> 5)] = ball;
     }
   }
 }
 
 extern "C" {
 
-size_t pcs_edt_workspace_bytes(int B, int H, int W) { return pcs_align256((size_t)B * H * W * 2); }
+size_t pcs_edt_workspace_bytes(int B, int H, int W) {
+  size_t NB = (H + 31) / 32, Wp = (size_t)pcs_words(W) * 32;
+  return pcs_align256(B * NB * Wp * 4) + 2 * pcs_align256(B * NB * Wp * 2) + pcs_align256((size_t)B * H);
+}
 
 int pcs_edt_bits(const uint32_t* bits, int invert, int B, int H, int W, double* dist, int32_t* sq, uint32_t* thr_bits,
                  int thr_sq, void* ws, size_t ws_bytes, void* stream) {
   PCS_REQUIRE(B >= 1 && H >= 1 && W >= 1, "empty batch or image");
   PCS_REQUIRE(H <= 16384 && W <= 16384, "image side above 16384 is not supported");
+  PCS_REQUIRE(B <= 65535, "batch above 65535");
   PCS_REQUIRE(dist || sq || thr_bits, "no output requested");
   if (ws == nullptr || ws_bytes < pcs_edt_workspace_bytes(B, H, W)) {
     pcs_set_error("EDT workspace too small (see pcs_edt_workspace_bytes)");
     return PCS_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  const int WW = pcs_words(W);
-  uint16_t* g = (uint16_t*)ws;
+  const int WW = pcs_words(W), Wp = WW << 5, NB = (H + 31) / 32;
+  PCS_REQUIRE((long long)NB <= 65535, "too many row bands");
+  int nwarps = EDT_WARPS;  // far-field solve: one row buffer pair (4 * Wp bytes) per warp in shared memory
+  while (nwarps > 1 && (size_t)nwarps * 4 * Wp > 200 * 1024) nwarps >>= 1;
+  size_t smem = (size_t)nwarps * 4 * Wp;
+  char* p = (char*)ws;
+  uint32_t* vw = (uint32_t*)p;
+  p += pcs_align256((size_t)B * NB * Wp * 4);
+  uint16_t* up = (uint16_t*)p;
+  p += pcs_align256((size_t)B * NB * Wp * 2);
+  uint16_t* dn = (uint16_t*)p;
+  p += pcs_align256((size_t)B * NB * Wp * 2);
+  uint8_t* row_far = (uint8_t*)p;
+  cudaMemsetAsync(row_far, 0, (size_t)B * H, st);
+  PCS_LAUNCH("k_edt_transpose", st,
+             k_edt_transpose<<<pcs_blocks((long long)B * NB * WW * 32, 256), 256, 0, st>>>(bits, invert, vw, B, H, W, WW, NB));
   dim3 gc((W + 127) / 128, B);
-  PCS_LAUNCH("k_edt_cols", st, k_edt_cols<<<gc, 128, 0, st>>>(bits, invert, g, H, W, WW));
+  PCS_LAUNCH("k_edt_carry", st, k_edt_carry<<<gc, 128, 0, st>>>(vw, up, dn, W, Wp, NB));
+  dim3 gn((W + EDT_TW - 1) / EDT_TW, NB, B);
+  PCS_LAUNCH("k_edt_near", st,
+             k_edt_near<<<gn, EDT_TW, 0, st>>>(vw, up, dn, dist, sq, thr_bits, thr_sq, row_far, H, W, WW, NB));
   int W2 = 1, L = 0;
   while (W2 <= W) {
     W2 <<= 1;
     ++L;
   }
-  size_t smem = (size_t)W * 4;
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
-    cudaFuncSetAttribute(k_edt_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_edt_far, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     smem_set = smem;
   }
-  dim3 gr(H, B);
-  PCS_LAUNCH("k_edt_rows", st, k_edt_rows<<<gr, EDT_ROW_THREADS, smem, st>>>(g, dist, sq, thr_bits, thr_sq, H, W, WW, W2, L));
+  dim3 gf((H + nwarps - 1) / nwarps, B);
+  PCS_LAUNCH("k_edt_far", st,
+             k_edt_far<<<gf, nwarps * 32, smem, st>>>(vw, up, dn, dist, sq, thr_bits, thr_sq, row_far, H, W, WW, NB, W2, L));
   return pcs_check_launch("edt");
 }
 

@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(MED_TX* MED_TY)
   const int tw = MED_TX + 2 * r, th = MED_TY + 2 * r;
   for (int i = threadIdx.y * MED_TX + threadIdx.x; i < tw * th; i += MED_TX * MED_TY) {
     int ty = i / tw, tx = i % tw;
-    int yy = pcs_reflect(y0 + ty - r, H), xx = pcs_reflect(x0 + tx - r, W);
+    // tile cells far outside the image (partial edge tiles) are never read back: clamp them
+    int yy = min(max(pcs_reflect(y0 + ty - r, H), 0), H - 1), xx = min(max(pcs_reflect(x0 + tx - r, W), 0), W - 1);
     tile[ty][tx] = src[(long long)yy * W + xx];
   }
   __syncthreads();

@@ -19,7 +19,7 @@
 #include "pcs.h"
 
 #define PROPS_THREADS 128
-#define PROPS_ROWS 16
+#define PROPS_ROWS 8
 #define T_AREA 0
 #define T_SUMY 1
 #define T_SUMX 2
@@ -89,10 +89,17 @@ __global__ void __launch_bounds__(PROPS_THREADS)
   const bool has_int = intensity != nullptr, has_ov = ov_bits != nullptr;
   RegionAcc acc;
   acc.label = 0;
-  const int y1 = min(H, (strip + 1) * PROPS_ROWS);
-  for (int y = strip * PROPS_ROWS; y < y1; ++y) {
+  const int y0 = strip * PROPS_ROWS;
+  // all foreground words of the strip first: one round trip instead of PROPS_ROWS dependent ones
+  uint32_t fw[PROPS_ROWS];
+#pragma unroll
+  for (int r = 0; r < PROPS_ROWS; ++r)
+    fw[r] = (y0 + r < H) ? (fg_bits ? __ldg(fg_bits + (b * H + y0 + r) * (long long)WW + k) : 0xffffffffu) : 0u;
+#pragma unroll 1
+  for (int r = 0; r < PROPS_ROWS; ++r) {
+    if (fw[r] == 0u) continue;
+    const int y = y0 + r;
     const long long wi = (b * H + y) * (long long)WW + k;
-    if (fg_bits && fg_bits[wi] == 0u) continue;
     const LabT* lrow = labels + (b * H + y) * (long long)W + x0;
     int L[32];
     if (sizeof(LabT) == 4 && n == 32 && ((((uintptr_t)lrow) & 15) == 0)) {
@@ -111,8 +118,19 @@ __global__ void __launch_bounds__(PROPS_THREADS)
     int I[32];
     if (has_int) {
       const IntT* irow = intensity + (b * H + y) * (long long)W + x0;
+      if (n == 32 && ((((uintptr_t)irow) & 15) == 0)) {
+        constexpr int VEC = 16 / sizeof(IntT);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) I[i] = (i < n && L[i] != 0) ? (int)irow[i] : 0;
+        for (int v = 0; v < 32 / VEC; ++v) {
+          uint4 q = __ldg(reinterpret_cast<const uint4*>(irow) + v);
+          const IntT* e = reinterpret_cast<const IntT*>(&q);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) I[v * VEC + i] = L[v * VEC + i] != 0 ? (int)e[i] : 0;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) I[i] = (i < n && L[i] != 0) ? (int)irow[i] : 0;
+      }
     }
     const uint32_t ovw = has_ov ? ov_bits[wi] : 0u;
     int runlab = 0, runstart = 0;

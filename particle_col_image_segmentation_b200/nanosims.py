@@ -64,7 +64,7 @@ def boundary_pixels(mask):
     inner = ops.erode(bits, W, cross, border_value=0)
     edge = ops.logic(bits, inner, "andnot", W)
     m = ops.unpack(edge, W, torch.bool)[0]
-    return torch.nonzero(m).to(torch.float64) + 1.0
+    return (torch.nonzero(m).to(torch.float64) + 1.0).contiguous()  # nonzero() hands back a transposed view
 
 
 def analyse(planes, red_mask, green_mask, agg_mask, raster=19.0, acq=512.0):

@@ -362,6 +362,7 @@ def roi_sums(labels, planes, n_rois):
 
 
 def min_dist(a_xy, b_xy):
+    a_xy, b_xy = a_xy.contiguous(), b_xy.contiguous()
     out = torch.empty(int(a_xy.shape[0]), dtype=torch.float64, device=a_xy.device)
     _lib.call("pcs_min_dist_f64", _p(a_xy), int(a_xy.shape[0]), _p(b_xy), int(b_xy.shape[0]), _p(out), _stream())
     return out
