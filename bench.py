@@ -42,6 +42,7 @@ KERNEL_BYTES_PER_VOXEL = {
     "k_ccl_mark": 0.125,
     "k_ccl_select": 0.25,
     "k_region_table": 4.0 + 2.0,
+    "k_region_table_bits": 4.0 + 2.0,
     "k_select_by_area": 0.25,
     "k_edt_transpose": 0.25,
     "k_edt_carry": 0.25,

@@ -139,6 +139,18 @@ int pcs_roi_sums_f64(const int32_t* labels, const double* planes, int K, int64_t
 /* out[i] = min_j |a_i - b_j| for (x, y) float64 pairs (pdist2 + min, .m:260-263, :301-304) */
 int pcs_min_dist_f64(const double* a, int64_t na, const double* b, int64_t nb, double* out, void* stream);
 
+/* ---- the whole segment pipeline for one chunk of slices -----------------------------------
+ * threshold (Otsu) -> size x size binary median -> label (8-connected) -> per-label table ->
+ * small objects (< min_size) out, holes filled -> exact EDT.  Stands in for the chain
+ * split_zstack.py:52 (slice loop) -> tiff_analysis.py:643, :743, :746, :769-773, :880 ->
+ * refine_boundaries.py:60; CPU statement: oracle/pipeline.py.  Outputs: mask / refined uint8,
+ * labels int32, edt float64 (all (B, H, W)), thr / counts int32[B], offsets int32[B+1],
+ * table int64[PCS_TABLE_COLS][cap]. */
+size_t pcs_segment_workspace_bytes(int B, int H, int W);
+int pcs_segment_chunk(const uint16_t* img, int B, int H, int W, int denoise_size, int min_size, uint8_t* mask, int32_t* labels,
+                      uint8_t* refined, double* edt, int32_t* thr, int32_t* counts, int32_t* offsets, int64_t* table,
+                      int64_t cap, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -116,6 +116,164 @@ __global__ void __launch_bounds__(PCS_CCL_THREADS) k_ccl_merge(P prov, int* __re
   }
 }
 
+// ---------------------------------------------------------------- tile-local union-find
+// CTA = CCL_TR rows x 32 words (1024 pixels).  Every run of the tile gets a slot in a shared
+// parent array (16 slots per word, ordered like the raster), unions between runs of the same
+// tile are resolved with shared-memory atomics, and each node leaves the kernel pointing at
+// the global index of its tile-local root.  Only adjacencies that cross a tile edge remain for
+// the global pass (k_ccl_merge_edges), so a component spanning the image costs a chain over
+// tiles, not over pixels or rows.
+// binary masks have at most 16 runs per 32-pixel word, multi-valued images up to 32: both tile shapes
+// (16 rows x 16 slots, 8 rows x 32 slots) use 32 KB of shared parents
+template <class P> struct PcsTile { static constexpr int TR = 16, LOG_SPW = 4; };
+template <> struct PcsTile<PcsGenProv> { static constexpr int TR = 8, LOG_SPW = 5; };
+
+__device__ __forceinline__ int pcs_lfind(volatile int* sp, int n) {
+  int r = n, p = sp[r];
+  while (p != r) {
+    r = p;
+    p = sp[r];
+  }
+  return r;
+}
+
+__device__ __forceinline__ void pcs_lunion(int* sp, int a, int b) {
+  while (true) {
+    a = pcs_lfind(sp, a);
+    b = pcs_lfind(sp, b);
+    if (a == b) return;
+    if (a < b) {
+      int t = a;
+      a = b;
+      b = t;
+    }
+    int old = atomicMin(sp + a, b);
+    if (old == a) return;
+    a = old;
+  }
+}
+
+template <class P, int CONN>
+__global__ void __launch_bounds__(PcsTile<P>::TR * 32) k_ccl_tile(P prov, int* __restrict__ parent) {
+  constexpr int CCL_TR = PcsTile<P>::TR, LSPW = PcsTile<P>::LOG_SPW, SPW = 1 << LSPW;
+  __shared__ int sp[CCL_TR * 32 * SPW];
+  __shared__ uint32_t ssm[CCL_TR][32];
+  const int H = prov.H, WW = prov.WW;
+  const int lane = threadIdx.x & 31, r = threadIdx.x >> 5;
+  const int k0 = blockIdx.x << 5, y0 = blockIdx.y * CCL_TR;
+  const long long b = blockIdx.z;
+  const int k = k0 + lane, y = y0 + r;
+  P p = prov.slice(b);
+  PcsConnWords c;
+  c.F = c.S = 0;
+  const bool in = y < H && k < WW;
+  if (in) p.FS(y, k, c.F, c.S);
+  ssm[r][lane] = c.S;
+  const int sbase = (r * 32 + lane) << LSPW;
+  {
+    uint32_t S = c.S;
+    int j = 0;
+    while (S) {
+      S &= S - 1;
+      sp[sbase + j] = sbase + j;
+      ++j;
+    }
+  }
+  __syncthreads();
+  if (c.F) {
+    p.conn(y, k, c);
+    if (c.J && lane > 0) pcs_lunion(sp, sbase, sbase - SPW + __popc(ssm[r][lane - 1]) - 1);
+    if (r > 0 && (c.U | c.UL | c.UR)) {
+      uint32_t S = c.S;
+      int j = 0;
+      while (S) {
+        int s;
+        uint32_t R = pcs_pop_run(c.F, S, s);
+        unsigned long long T = ((unsigned long long)(c.U & R)) << 1;
+        if (CONN == 8) T |= (unsigned long long)(c.UL & R) | (((unsigned long long)(c.UR & R)) << 2);
+        while (T) {
+          int i = __ffsll((long long)T) - 1;
+          T &= T + (1ull << i);
+          int rel = (i - 1) >> 5;
+          int ka = lane + rel;
+          if (ka >= 0 && ka < 32) {  // the run above lives in this tile
+            int ja = (i - 1) & 31;
+            uint32_t Sa = c.Sa[rel + 1];
+            int sa = pcs_start_at_or_below(Sa, ja);
+            int ord = __popc(Sa & ((1u << sa) - 1u));
+            pcs_lunion(sp, sbase + j, (((r - 1) * 32 + ka) << LSPW) + ord);
+          }
+        }
+        ++j;
+      }
+    }
+  }
+  __syncthreads();
+  if (c.S) {
+    const int Wp = WW << 5;
+    int* par = parent + b * (long long)H * Wp;
+    const int gbase = y * Wp + (k << 5);
+    uint32_t S = c.S;
+    int j = 0;
+    while (S) {
+      int s = __ffs(S) - 1;
+      S &= S - 1;
+      int root = pcs_lfind(sp, sbase + j);
+      int rw = root >> LSPW, rj = root & (SPW - 1);  // word slot (row * 32 + lane) and run ordinal of the root
+      int rr = rw >> 5, rk = rw & 31;
+      int rs = __fns(ssm[rr][rk], 0, rj + 1);
+      par[gbase + s] = (y0 + rr) * Wp + ((k0 + rk) << 5) + rs;
+      ++j;
+    }
+  }
+}
+
+// thread per word: the unions k_ccl_tile could not do -- adjacencies across a tile edge
+template <class P, int CONN>
+__global__ void __launch_bounds__(PCS_CCL_THREADS) k_ccl_merge_edges(P prov, int* __restrict__ parent, int B) {
+  const int H = prov.H, WW = prov.WW;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)B * H * WW;
+  if (t >= total) return;
+  int k = (int)(t % WW);
+  int y = (int)((t / WW) % H);
+  constexpr int CCL_TR = PcsTile<P>::TR;
+  const bool top = (y % CCL_TR) == 0, left = (k & 31) == 0, right = (k & 31) == 31;
+  if (!(top || left || right)) return;
+  long long b = t / ((long long)WW * H);
+  P p = prov.slice(b);
+  uint32_t F0, S0;
+  p.FS(y, k, F0, S0);
+  if (!F0) return;
+  PcsConnWords c;
+  p.conn(y, k, c);
+  const int Wp = WW << 5;
+  int* par = parent + b * (long long)H * Wp;
+  const int base = y * Wp + (k << 5);
+  if (c.J && left) {
+    uint32_t Sl = p.Sword(y, k - 1);
+    pcs_uf_union(par, base, base - 32 + (31 - __clz(Sl)));
+  }
+  if (y == 0 || !(c.U | c.UL | c.UR)) return;
+  uint32_t S = c.S;
+  const int abase = (y - 1) * Wp + (k << 5);
+  while (S) {
+    int s;
+    uint32_t R = pcs_pop_run(c.F, S, s);
+    unsigned long long T = ((unsigned long long)(c.U & R)) << 1;
+    if (CONN == 8) T |= (unsigned long long)(c.UL & R) | (((unsigned long long)(c.UR & R)) << 2);
+    while (T) {
+      int i = __ffsll((long long)T) - 1;
+      T &= T + (1ull << i);
+      int rel = (i - 1) >> 5;
+      if (!(top || (rel < 0 && left) || (rel > 0 && right))) continue;  // done inside the tile
+      int ja = (i - 1) & 31;
+      int sa = pcs_start_at_or_below(c.Sa[rel + 1], ja);
+      pcs_uf_union(par, base + s, abase + rel * 32 + sa);
+    }
+  }
+}
+
 // warp per 32-word chunk: point every node at its root, flag roots, count them
 template <class P>
 __global__ void __launch_bounds__(PCS_CCL_THREADS)
@@ -449,11 +607,16 @@ static int ccl_forest(const P& prov, int B, int conn, const PcsCclWs& ws, int32_
   long long warps = (long long)B * H * CPR;
   unsigned gw = pcs_blocks(words, PCS_CCL_THREADS);
   unsigned gc = pcs_blocks(warps * 32, PCS_CCL_THREADS);
-  PCS_LAUNCH("k_ccl_init", st, k_ccl_init<P><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, B));
-  if (conn == 8)
-    PCS_LAUNCH("k_ccl_merge", st, k_ccl_merge<P, 8><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, B));
-  else
-    PCS_LAUNCH("k_ccl_merge", st, k_ccl_merge<P, 4><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, B));
+  constexpr int CCL_TR = PcsTile<P>::TR;
+  PCS_REQUIRE(B <= 65535 && (H + CCL_TR - 1) / CCL_TR <= 65535, "grid too large for the tile kernel");
+  dim3 gt((WW + 31) / 32, (H + CCL_TR - 1) / CCL_TR, B);
+  if (conn == 8) {
+    PCS_LAUNCH("k_ccl_tile", st, (k_ccl_tile<P, 8><<<gt, CCL_TR * 32, 0, st>>>(prov, ws.parent)));
+    PCS_LAUNCH("k_ccl_merge_edges", st, (k_ccl_merge_edges<P, 8><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, B)));
+  } else {
+    PCS_LAUNCH("k_ccl_tile", st, (k_ccl_tile<P, 4><<<gt, CCL_TR * 32, 0, st>>>(prov, ws.parent)));
+    PCS_LAUNCH("k_ccl_merge_edges", st, (k_ccl_merge_edges<P, 4><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, B)));
+  }
   PCS_LAUNCH("k_ccl_flatten", st, k_ccl_flatten<P><<<gc, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, ws.rootbits, ws.chunk, zero_aux ? ws.aux : nullptr, B, CPR));
   if (counts) {
     PCS_LAUNCH("k_ccl_scan", st, k_ccl_scan<<<B, 1024, 0, st>>>(ws.chunk, counts, H * CPR));

@@ -161,13 +161,23 @@ __global__ void __launch_bounds__(EDT_TW)
   const int q = blockIdx.y;
   const long long b = blockIdx.z;
   const long long band = (b * NB + q) * (long long)Wp;
+  // background pixels have g = 0: clear the tile, then visit only the foreground rows of each column
+  uint32_t* gz = reinterpret_cast<uint32_t*>(&g[0][0]);
+  for (int i = tid; i < 32 * EDT_TWH / 2; i += EDT_TW) gz[i] = 0u;
+  __syncthreads();
   for (int col = tid; col < EDT_TWH; col += EDT_TW) {
     const int x = x0 - EDT_HALO + col;
     if (x >= 0 && x < W) {
-      const uint32_t z = ~__ldg(vw + band + x);
-      const uint32_t cu = __ldg(up + band + x), cd = __ldg(dn + band + x);
-#pragma unroll 8
-      for (int r = 0; r < 32; ++r) g[r][col] = (uint16_t)edt_vdist(z, r, cu, cd);
+      uint32_t f = __ldg(vw + band + x);  // set bits = foreground rows of this column
+      if (f) {
+        const uint32_t z = ~f;
+        const uint32_t cu = __ldg(up + band + x), cd = __ldg(dn + band + x);
+        while (f) {
+          const int r = __ffs(f) - 1;
+          f &= f - 1;
+          g[r][col] = (uint16_t)edt_vdist(z, r, cu, cd);
+        }
+      }
     } else {
 #pragma unroll 8
       for (int r = 0; r < 32; ++r) g[r][col] = (uint16_t)EDT_INF;  // outside the image: no site
@@ -179,10 +189,21 @@ __global__ void __launch_bounds__(EDT_TW)
   const int rows = min(32, H - (q << 5));
   for (int r = 0; r < rows; ++r) {
     const int y = (q << 5) + r;
+    const uint32_t gx = x < W ? g[r][col] : 0u;
+    const long long o = (b * H + y) * (long long)W + x;
+    if (!__any_sync(0xffffffffu, gx != 0u)) {
+      // 32 background pixels in a row (the common case): plain zero stores
+      if (x < W) {
+        if (dist) dist[o] = 0.0;
+        if (sq) sq[o] = 0;
+      }
+      if (thr_bits && (tid & 31) == 0 && (x >> 5) < WW)
+        thr_bits[(b * H + y) * (long long)WW + (x >> 5)] = thr_sq >= 0 ? pcs_valid_mask(x >> 5, W) : 0u;
+      continue;
+    }
     uint32_t d2 = 0;
     bool far = false;
     if (x < W) {
-      const uint32_t gx = g[r][col];
       if (gx > EDT_DMAX) {
         far = true;
       } else if (gx != 0u) {
@@ -196,14 +217,13 @@ __global__ void __launch_bounds__(EDT_TW)
         d2 = best;
       }
       if (!far) {
-        const long long o = (b * H + y) * (long long)W + x;
-        if (dist) dist[o] = d2 ? sqrt((double)d2) : 0.0;
+        if (dist) dist[o] = sqrt((double)d2);
         if (sq) sq[o] = (int32_t)d2;
       }
     }
     if (__any_sync(0xffffffffu, far) && (tid & 31) == 0) row_far[b * H + y] = 1;
     if (thr_bits) {
-      unsigned ball = __ballot_sync(0xffffffffu, x < W && !far && d2 <= (uint32_t)thr_sq);
+      unsigned ball = __ballot_sync(0xffffffffu, x < W && !far && (int)d2 <= thr_sq);
       if ((tid & 31) == 0 && (x >> 5) < WW) thr_bits[(b * H + y) * (long long)WW + (x >> 5)] = ball;
     }
   }

@@ -175,6 +175,74 @@ __global__ void __launch_bounds__(PROPS_THREADS)
   acc_flush(acc, table, cap, base, has_int, has_ov);
 }
 
+// Binary-labelling fast path: the runs are read off the foreground bit image, so the label
+// image is touched once per RUN (4 bytes) instead of once per pixel, background words cost one
+// 4-byte load, and the register footprint stays small enough for full occupancy.
+template <typename IntT>
+__global__ void __launch_bounds__(PROPS_THREADS)
+    k_region_table_bits(const int32_t* __restrict__ labels, const IntT* __restrict__ intensity, const uint32_t* __restrict__ fg_bits,
+                        const uint32_t* __restrict__ ov_bits, const int* __restrict__ offsets, long long* __restrict__ table,
+                        long long cap, int B, int H, int W, int WW, int strips) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)B * strips * WW;
+  if (t >= total) return;
+  const int k = (int)(t % WW);
+  const int strip = (int)((t / WW) % strips);
+  const long long b = t / ((long long)WW * strips);
+  const long long base = offsets ? (long long)offsets[b] : 0;
+  const int x0 = k << 5;
+  const bool has_int = intensity != nullptr, has_ov = ov_bits != nullptr;
+  const int y0 = strip * PROPS_ROWS;
+  uint32_t fw[PROPS_ROWS];
+#pragma unroll
+  for (int r = 0; r < PROPS_ROWS; ++r) fw[r] = (y0 + r < H) ? __ldg(fg_bits + (b * H + y0 + r) * (long long)WW + k) : 0u;
+  RegionAcc acc;
+  acc.label = 0;
+#pragma unroll
+  for (int r = 0; r < PROPS_ROWS; ++r) {
+    uint32_t f = fw[r];
+    if (f == 0u) continue;
+    const int y = y0 + r;
+    const long long rowo = (b * H + y) * (long long)W + x0;
+    const uint32_t ovw = has_ov ? ov_bits[(b * H + y) * (long long)WW + k] : 0u;
+    uint32_t S = f & ~(f << 1);
+    while (S) {
+      const int s = __ffs(S) - 1;
+      S &= S - 1;
+      const uint32_t upper = ~(f >> s);
+      const int len = upper ? (__ffs(upper) - 1) : 32;
+      const int lab = labels[rowo + s];
+      const int xs = x0 + s;
+      long long si = 0;
+      if (has_int)
+        for (int i = 0; i < len; ++i) si += (long long)intensity[rowo + s + i];
+      if (lab != acc.label) {
+        acc_flush(acc, table, cap, base, has_int, has_ov);
+        acc.label = lab;
+        acc.area = 0;
+        acc.sx = acc.sy = acc.si = 0;
+        acc.minx = xs;
+        acc.maxx = xs + len - 1;
+        acc.miny = acc.maxy = y;
+        acc.first = (long long)y * W + xs;
+        acc.ov = 0;
+      }
+      acc.area += len;
+      acc.sx += (long long)len * xs + (long long)(len * (len - 1) / 2);
+      acc.sy += (long long)len * y;
+      acc.si += si;
+      acc.minx = min(acc.minx, xs);
+      acc.maxx = max(acc.maxx, xs + len - 1);
+      acc.maxy = y;
+      if (has_ov) {
+        const uint32_t rm = (len >= 32 ? 0xffffffffu : ((1u << len) - 1u)) << s;
+        acc.ov += __popc(ovw & rm);
+      }
+    }
+  }
+  acc_flush(acc, table, cap, base, has_int, has_ov);
+}
+
 // out bits = pixels whose label has keep[label] != 0 (per-slice LUT rows of `lut_stride` entries)
 template <typename LabT>
 __global__ void __launch_bounds__(256)
@@ -283,7 +351,17 @@ int pcs_region_table(const void* labels, int label_bytes, const void* intensity,
   if (intensity == nullptr) intensity_dtype = -1;
 #define LAUNCH(LT, IT) \
   PCS_LAUNCH("k_region_table", st, (k_region_table<LT, IT><<<g, PROPS_THREADS, 0, st>>>((const LT*)labels, (const IT*)intensity, fg_bits, ov_bits, offsets, tb, cap, B, H, W, WW, strips)))
-  if (label_bytes == 4) {
+  if (label_bytes == 4 && fg_bits != nullptr) {
+    // binary labelling: runs come from the bit image
+    if (intensity_dtype == 1)
+      PCS_LAUNCH("k_region_table_bits", st, (k_region_table_bits<uint16_t><<<g, PROPS_THREADS, 0, st>>>((const int32_t*)labels, (const uint16_t*)intensity, fg_bits, ov_bits, offsets, tb, cap, B, H, W, WW, strips)));
+    else if (intensity_dtype == 0 || intensity_dtype == -1)
+      PCS_LAUNCH("k_region_table_bits", st, (k_region_table_bits<uint8_t><<<g, PROPS_THREADS, 0, st>>>((const int32_t*)labels, (const uint8_t*)intensity, fg_bits, ov_bits, offsets, tb, cap, B, H, W, WW, strips)));
+    else {
+      pcs_set_error("unsupported intensity dtype");
+      return PCS_ERR_UNSUPPORTED;
+    }
+  } else if (label_bytes == 4) {
     if (intensity_dtype == 1)
       LAUNCH(int32_t, uint16_t);
     else if (intensity_dtype == 0 || intensity_dtype == -1)

@@ -118,42 +118,22 @@ def segment_zstack_device(stack, denoise_size=5, min_size=20, chunk=16, max_regi
     lib = _lib.load()
     st = ops._stream()
     P = ops._p
+    dn = int(denoise_size or 0)
+    ms = int(min_size or 0)
     for a in range(0, Z, chunk):
         b = min(Z, a + chunk)
         B = b - a
-        img = stack[a:b]
-        WW = ops.words(W)
-        # K1: histogram + Otsu, K2: threshold, K3: 5x5 median of the binary image
-        hist = torch.empty((B, 65536), dtype=torch.int32, device=dev)
-        thr = out.threshold[a:b]
-        _lib.check(lib.pcs_histogram_u16(P(img), P(hist), B, H, W, st), "histogram")
-        _lib.check(lib.pcs_otsu_u16(P(hist), P(thr), 0, B, H * W, st), "otsu")
-        raw = torch.empty((B, H, WW), dtype=torch.int32, device=dev)
-        _lib.check(lib.pcs_compare_u16(P(img), 0, P(thr), 0, P(raw), 0, B, H, W, st), "threshold")
-        if denoise_size and denoise_size > 1:
-            bits = torch.empty_like(raw)
-            _lib.check(lib.pcs_majority_bits(P(raw), P(bits), denoise_size, B, H, W, st), "median")
-        else:
-            bits = raw
-        _lib.check(lib.pcs_unpack_bits(P(bits), P(out.mask[a:b]), B, H, W, st), "mask out")
-        # K4: labels (8-connected, raster order), K8: per-label table
-        labels = out.labels[a:b]
-        counts = out.counts[a:b]
         offsets = torch.empty(B + 1, dtype=torch.int32, device=dev)
-        nws = lib.pcs_ccl_workspace_bytes(B, H, W, 0)
-        ws = ops._ws(nws, dev, "ccl")
-        _lib.check(lib.pcs_label_bits(P(bits), B, H, W, 8, 0, P(labels), 4, P(counts), P(offsets), 0, 0, P(ws), nws, st), "label")
-        table = ops.new_table(max_regions_per_slice * B, dev)
-        ops.region_table(labels, offsets, table, intensity=img, fg_bits=bits)
-        # refine: small objects out (area from the table), holes filled
-        keep = ops.select_by_area(labels, bits, table, offsets, min_size) if min_size and min_size > 1 else bits
-        refined_bits = torch.empty_like(keep)
-        _lib.check(lib.pcs_fill_holes_bits(P(keep), P(refined_bits), B, H, W, P(ws), nws, st), "fill holes")
-        _lib.check(lib.pcs_unpack_bits(P(refined_bits), P(out.refined[a:b]), B, H, W, st), "refined out")
-        # K7: exact EDT of the refined mask
-        nwe = lib.pcs_edt_workspace_bytes(B, H, W)
-        wse = ops._ws(nwe, dev, "edt")
-        _lib.check(lib.pcs_edt_bits(P(refined_bits), 0, B, H, W, P(out.edt[a:b]), 0, 0, 0, P(wse), nwe, st), "edt")
+        cap = max_regions_per_slice * B
+        table = torch.empty((ops.TABLE_COLS, cap), dtype=torch.int64, device=dev)
+        nws = lib.pcs_segment_workspace_bytes(B, H, W)
+        ws = ops._ws(nws, dev, "segment")
+        # one C-ABI call per chunk: histogram + Otsu, threshold, median, labels, table, refine, EDT
+        _lib.check(
+            lib.pcs_segment_chunk(P(stack[a:b]), B, H, W, dn, ms, P(out.mask[a:b]), P(out.labels[a:b]), P(out.refined[a:b]), P(out.edt[a:b]),
+                                  P(out.threshold[a:b]), P(out.counts[a:b]), P(offsets), P(table), cap, P(ws), nws, st),
+            "pcs_segment_chunk",
+        )
         out.tables.append((a, offsets, table))
     return out
 
