@@ -59,12 +59,13 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--slices", type=int, default=64, help="slices per GPU (configs[1]: 64; north_star target: 256)")
     ap.add_argument("--size", type=int, default=2048)
-    ap.add_argument("--chunk", type=int, default=16, help="slices per batched launch")
+    ap.add_argument("--chunk", type=int, default=64, help="slices per batched launch")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-sample", type=int, default=0, help="slices in the CPU baseline sample (0 = one per host core, at most 32)")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a captured CUDA graph")
     return ap.parse_args()
 
 
@@ -228,30 +229,33 @@ def run_b200(args):
     lib = _lib.load()
 
     stack = synth.zstack_u16_device(Z, S, S, seed=1002 + rank, device=dev)
-    res = None
+    # the pipeline bound to this stack; eager launches for the profiled pass, a captured CUDA
+    # graph (same kernels, same order) for the timed pass
+    plan_eager = split_zstack.SegmentPlan(stack, chunk=args.chunk, z0=rank * Z)
+    res = plan_eager.out
+    plan = split_zstack.SegmentPlan(stack, chunk=args.chunk, z0=rank * Z, out=None, graph=True) if not args.no_graph else plan_eager
 
-    def step():
-        nonlocal res
-        res = split_zstack.segment_zstack_device(stack, chunk=args.chunk, out=res, z0=rank * Z)
-        table = res.table_device()
+    def step(p=None):
+        r = (p or plan)()
+        table = r.table_device()
         if world > 1:
             table = pdist.gather_tables(table)
-        return table
+        return r, table
 
     # parity spot check against the oracle on one slice of this very stack (outside the timed region)
     parity = None
     if rank == 0:
-        table = step()
+        r, table = step()
         torch.cuda.synchronize()
         zi = Z // 2
         want = opipe.segment_slice(stack[zi].cpu().numpy(), z=zi)
         got_tab = table[table[:, 0] == zi].cpu().numpy()
         parity = bool(
-            int(res.threshold[zi]) == want["threshold"]
-            and np.array_equal(res.mask[zi].cpu().numpy().astype(bool), want["mask"])
-            and np.array_equal(res.labels[zi].cpu().numpy(), want["labels"])
-            and np.array_equal(res.refined[zi].cpu().numpy().astype(bool), want["refined"])
-            and np.array_equal(res.edt[zi].cpu().numpy(), want["edt"])
+            int(r.threshold[zi]) == want["threshold"]
+            and np.array_equal(r.mask[zi].cpu().numpy().astype(bool), want["mask"])
+            and np.array_equal(r.labels[zi].cpu().numpy(), want["labels"])
+            and np.array_equal(r.refined[zi].cpu().numpy().astype(bool), want["refined"])
+            and np.array_equal(r.edt[zi].cpu().numpy(), want["edt"])
             and np.array_equal(got_tab, want["table"])
         )
         if not parity:
@@ -262,32 +266,43 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(p, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            step(p)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps
+
     for _ in range(args.warmup):
         step()
-    barrier()
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = lib.pcs_kernel_launches()
-    if not args.no_profile:
-        lib.pcs_profile_enable(1)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        table = step()
-    e1.record()
-    barrier()
-    lib.pcs_profile_enable(0)
-    launches = lib.pcs_kernel_launches() - launches0
+    ms_step = timed(plan, args.steps)
     clocks = sampler.stop()
-    ms_total = e0.elapsed_time(e1)
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
+    # kernels per step: counted on an eager pass (a graph replay re-issues the captured launches)
+    for _ in range(1):
+        l0 = lib.pcs_kernel_launches()
+        step(plan_eager)
+        launches = (lib.pcs_kernel_launches() - l0) * args.steps
     voxels = float(Z) * S * S * world
     value = voxels / (ms_step * 1e-3) / 1e6
 
-    prof = {} if args.no_profile else collect_profile(lib)
+    # per-kernel CUDA-event timing: a second timed pass of the same K steps, launched eagerly with an
+    # event pair around every kernel on the launching stream (the events add a few percent to the step)
+    prof, ms_step_profiled = {}, None
+    if not args.no_profile:
+        lib.pcs_profile_enable(1)
+        ms_step_profiled = timed(plan_eager, args.steps)
+        lib.pcs_profile_enable(0)
+        prof = collect_profile(lib)
+    del launches0
 
     # end to end through the public API with host buffers (pinned), copies inside the timed region
     e2e = None
@@ -325,7 +340,8 @@ def run_b200(args):
         avg_ms = kms / kcnt
         achieved = bpv * per_launch_vox / (avg_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "bytes_per_voxel": bpv, "avg_launch_ms": avg_ms, "launches": kcnt, "peak_source": peak_src, "kernel_time_share": shares}
+                "bytes_per_voxel": bpv, "avg_launch_ms": avg_ms, "launches": kcnt, "peak_source": peak_src, "kernel_time_share": shares,
+                "timed": "per-kernel CUDA events on the launching stream over a second pass of the same K steps (eager launches)", "ms_per_step_with_events": ms_step_profiled}
     per_gpu = value / world * 1e6
     line = {
         "metric": METRIC,
@@ -340,7 +356,7 @@ def run_b200(args):
         "vs_baseline": None,
         "dtype": "u16",
         "data": "synthetic",
-        "config": {"workload": f"split_zstack + segment a synthetic {S}x{S}x{Z} uint16 z-stack per GPU (BASELINE.json configs[1])", "size": S, "slices_per_gpu": Z, "chunk": args.chunk,
+        "config": {"workload": f"split_zstack + segment a synthetic {S}x{S}x{Z} uint16 z-stack per GPU (BASELINE.json configs[1])", "size": S, "slices_per_gpu": Z, "chunk": args.chunk, "launch": "eager" if args.no_graph else "cuda graph replay (one graph per step)",
                    "l2": "input stack (%.0f MiB) and outputs are larger than L2; no flush needed" % (Z * S * S * 2 / 2**20), "parity_spot_check": parity},
         "clocks": clocks,
         "e2e": e2e,

@@ -77,6 +77,8 @@ int pcs_otsu_u16(const uint32_t* hist, int32_t* thr, int32_t* minmax, int B, int
  * size in {3, 5, 7}.  pcs_majority_bits is the same filter on a binary image. */
 int pcs_median_u8(const uint8_t* img, uint8_t* out, int size, int B, int H, int W, void* stream);
 int pcs_majority_bits(const uint32_t* in, uint32_t* out, int size, int B, int H, int W, void* stream);
+/* same, also writing the result as a uint8 0/1 image (fused) */
+int pcs_majority_bits_mask(const uint32_t* in, uint32_t* out, uint8_t* mask, int size, int B, int H, int W, void* stream);
 
 /* ---- K4: connected-component labelling -----------------------------------------
  * skimage.measure.label / scipy.ndimage.label (tiff_analysis.py:260, :743, :829;
@@ -99,6 +101,13 @@ int pcs_label_conn(const uint32_t* planes, int B, int H, int W, int connectivity
 /* ---- K6 and friends on the same forest ------------------------------------------
  * scipy.ndimage.binary_fill_holes (tiff_analysis.py:880) */
 int pcs_fill_holes_bits(const uint32_t* bits, uint32_t* out, int B, int H, int W, void* ws, size_t ws_bytes, void* stream);
+/* the same result when the 8-connected components of `bits` with area >= min_size are described by a
+ * region table (bounding boxes): only background inside a box is labelled (holes lie inside their
+ * component's box), which is what the pipeline uses */
+size_t pcs_fill_holes_table_workspace_bytes(int B, int H, int W);
+int pcs_fill_holes_table_bits(const uint32_t* bits, const int64_t* table, int64_t cap, const int32_t* offsets, int64_t min_size,
+                              uint32_t* out, uint8_t* out_mask /* optional uint8 copy */, int B, int H, int W, void* ws, size_t ws_bytes,
+                              void* stream);
 /* skimage.morphology.remove_small_objects (area filter of tiff_analysis.py:769-773); ws needs with_aux = 1 */
 int pcs_remove_small_bits(const uint32_t* bits, uint32_t* out, int B, int H, int W, int connectivity, int min_size, void* ws, size_t ws_bytes, void* stream);
 /* components of `bits` that contain a seed pixel (merged_image, tiff_analysis.py:843-878) */

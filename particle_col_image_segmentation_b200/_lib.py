@@ -46,12 +46,15 @@ SIGNATURES = {
     "pcs_otsu_u16": (c_int, [_P, _P, _P, _I, _L, _P]),
     "pcs_median_u8": (c_int, [_P, _P, _I, _I, _I, _I, _P]),
     "pcs_majority_bits": (c_int, [_P, _P, _I, _I, _I, _I, _P]),
+    "pcs_majority_bits_mask": (c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "pcs_ccl_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "pcs_label_bits": (c_int, [_P, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P, _L, _P, _Z, _P]),
     "pcs_conn_planes_bytes": (_Z, [_I, _I, _I]),
     "pcs_conn_planes": (c_int, [_P, _I, _P, _P, _I, _I, _I, _I, _I, _P]),
     "pcs_label_conn": (c_int, [_P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _L, _P, _Z, _P]),
     "pcs_fill_holes_bits": (c_int, [_P, _P, _I, _I, _I, _P, _Z, _P]),
+    "pcs_fill_holes_table_workspace_bytes": (_Z, [_I, _I, _I]),
+    "pcs_fill_holes_table_bits": (c_int, [_P, _P, _L, _P, _L, _P, _P, _I, _I, _I, _P, _Z, _P]),
     "pcs_remove_small_bits": (c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _Z, _P]),
     "pcs_select_components_bits": (c_int, [_P, _P, _P, _I, _I, _I, _I, _P, _Z, _P]),
     "pcs_local_maxima_conn": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _Z, _P]),

@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(PCS_CCL_THREADS)
 template <class P>
 __global__ void __launch_bounds__(PCS_CCL_THREADS)
     k_ccl_select(P prov, const int* __restrict__ parent, int want_marked, const uint32_t* __restrict__ or_bits,
-                 const int32_t* __restrict__ veto_counts, uint32_t* __restrict__ out, int B) {
+                 const int32_t* __restrict__ veto_counts, uint32_t* __restrict__ out, uint8_t* __restrict__ mask, int B) {
   const int H = prov.H, WW = prov.WW;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)B * H * WW;
@@ -596,6 +596,69 @@ __global__ void __launch_bounds__(PCS_CCL_THREADS)
   }
   if (or_bits) o |= or_bits[t];
   out[t] = o;
+  if (mask) pcs_store_mask_bytes(mask + (b * H + y) * (long long)prov.W, k, prov.W, o);  // fused uint8 output
+}
+
+// ---------------------------------------------------------------- hole filling inside bounding boxes
+// A hole of an (8-connected) component lies inside that component's bounding box, so background
+// outside every box is open by construction and never needs labelling.  k_bbox_raster paints the
+// boxes of the kept components (area >= min_size) from the region table; k_hole_candidates turns
+// them into the candidate mask C (background inside a box) and the seed mask M (candidates on the
+// image border or 4-adjacent to open background).  Holes = 4-connected components of C without a seed.
+__global__ void __launch_bounds__(256)
+    k_bbox_raster(const long long* __restrict__ table, long long cap, const int* __restrict__ offsets, long long min_size,
+                  uint32_t* __restrict__ bb, int B, int H, int WW) {
+  long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // warp per table row
+  const int lane = threadIdx.x & 31;
+  const long long nrows = min((long long)offsets[B], cap);
+  if (g >= nrows) return;
+  if (table[0 * cap + g] < min_size) return;  // column 0: area
+  int lo = 0, hi = B;                          // slice of this row: offsets[b] <= g < offsets[b+1]
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if ((long long)offsets[mid] <= g) lo = mid; else hi = mid;
+  }
+  const int y0 = (int)table[3 * cap + g], x0 = (int)table[4 * cap + g];
+  const int y1 = (int)table[5 * cap + g], x1 = (int)table[6 * cap + g];  // inclusive
+  const int k0 = x0 >> 5, k1 = x1 >> 5;
+  uint32_t* base = bb + (long long)lo * H * WW;
+  const int nw = k1 - k0 + 1;
+  const long long cells = (long long)(y1 - y0 + 1) * nw;
+  for (long long i = lane; i < cells; i += 32) {
+    const int y = y0 + (int)(i / nw), k = k0 + (int)(i % nw);
+    uint32_t m = 0xffffffffu;
+    if (k == k0) m &= 0xffffffffu << (x0 & 31);
+    if (k == k1) m &= 0xffffffffu >> (31 - (x1 & 31));
+    atomicOr(base + (long long)y * WW + k, m);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    k_hole_candidates(const uint32_t* __restrict__ fbits, const uint32_t* __restrict__ bb, uint32_t* __restrict__ cand,
+                      uint32_t* __restrict__ seed, int B, int H, int W, int WW) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)B * H * WW;
+  if (t >= total) return;
+  const int k = (int)(t % WW);
+  const int y = (int)((t / WW) % H);
+  const uint32_t vm = pcs_valid_mask(k, W);
+  const uint32_t box = bb[t];
+  const uint32_t C = ~fbits[t] & box & vm;
+  cand[t] = C;
+  uint32_t M = 0;
+  if (C) {
+    // open background = background outside every box; outside the image counts as open too
+    auto open_at = [&](long long idx, int kk) { return ~fbits[idx] & ~bb[idx] & pcs_valid_mask(kk, W); };
+    const uint32_t n_c = ~fbits[t] & ~box & vm;
+    uint32_t adj = (n_c << 1) | (n_c >> 1);
+    adj |= (k > 0) ? (open_at(t - 1, k - 1) >> 31) : 1u;
+    if (k + 1 < WW) adj |= open_at(t + 1, k + 1) << 31;
+    adj |= (y > 0) ? open_at(t - WW, k) : 0xffffffffu;
+    adj |= (y + 1 < H) ? open_at(t + WW, k) : 0xffffffffu;
+    adj |= 1u << ((W - 1) & 31) & ((k == WW - 1) ? 0xffffffffu : 0u);  // right image border
+    M = C & adj;
+  }
+  seed[t] = M;
 }
 
 // ============================================================== host drivers
@@ -689,8 +752,44 @@ int pcs_fill_holes_bits(const uint32_t* bits, uint32_t* out, int B, int H, int W
   if (rc) return rc;
   unsigned gw = pcs_blocks((long long)B * H * prov.WW, PCS_CCL_THREADS);
   PCS_LAUNCH("k_ccl_mark", st, k_ccl_mark<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, nullptr, 0, B));
-  PCS_LAUNCH("k_ccl_select", st, k_ccl_select<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, 0, bits, nullptr, out, B));
+  PCS_LAUNCH("k_ccl_select", st, k_ccl_select<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, 0, bits, nullptr, out, nullptr, B));
   return pcs_check_launch("fill holes");
+}
+
+int pcs_fill_holes_table_bits(const uint32_t* bits, const int64_t* table, int64_t cap, const int32_t* offsets, int64_t min_size,
+                              uint32_t* out, uint8_t* out_mask, int B, int H, int W, void* wsp, size_t ws_bytes, void* stream) {
+  int rc = check_dims(B, H, W);
+  if (rc) return rc;
+  PCS_REQUIRE(bits && table && offsets && out, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int WW = pcs_words(W);
+  const size_t plane = pcs_align256((size_t)B * H * WW * 4);
+  const size_t need = pcs_ccl_ws_bytes(B, H, W, 0) + 3 * plane;
+  if (wsp == nullptr || ws_bytes < need) {
+    pcs_set_error("fill-holes workspace too small (see pcs_fill_holes_table_workspace_bytes)");
+    return PCS_ERR_WORKSPACE;
+  }
+  PcsCclWs ws;
+  rc = pcs_ccl_ws_carve(wsp, ws_bytes, B, H, W, 0, &ws);
+  if (rc) return rc;
+  char* extra = (char*)wsp + pcs_ccl_ws_bytes(B, H, W, 0);
+  uint32_t* bb = (uint32_t*)extra;
+  uint32_t* cand = (uint32_t*)(extra + plane);
+  uint32_t* seed = (uint32_t*)(extra + 2 * plane);
+  cudaMemsetAsync(bb, 0, (size_t)B * H * WW * 4, st);
+  PCS_LAUNCH("k_bbox_raster", st, k_bbox_raster<<<pcs_blocks(cap * 32, 256), 256, 0, st>>>((const long long*)table, cap, offsets, min_size, bb, B, H, WW));
+  unsigned gw = pcs_blocks((long long)B * H * WW, PCS_CCL_THREADS);
+  PCS_LAUNCH("k_hole_candidates", st, k_hole_candidates<<<gw, 256, 0, st>>>(bits, bb, cand, seed, B, H, W, WW));
+  PcsBinProv prov{cand, H, W, WW, 0};
+  rc = ccl_forest(prov, B, 4, ws, nullptr, 0, st);
+  if (rc) return rc;
+  PCS_LAUNCH("k_ccl_mark", st, (k_ccl_mark<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, seed, 1, B)));
+  PCS_LAUNCH("k_ccl_select", st, (k_ccl_select<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, 0, bits, nullptr, out, out_mask, B)));
+  return pcs_check_launch("fill holes (table)");
+}
+
+size_t pcs_fill_holes_table_workspace_bytes(int B, int H, int W) {
+  return pcs_ccl_ws_bytes(B, H, W, 0) + 3 * pcs_align256((size_t)B * H * pcs_words(W) * 4);
 }
 
 int pcs_remove_small_bits(const uint32_t* bits, uint32_t* out, int B, int H, int W, int connectivity, int min_size,
@@ -708,7 +807,7 @@ int pcs_remove_small_bits(const uint32_t* bits, uint32_t* out, int B, int H, int
   unsigned gw = pcs_blocks((long long)B * H * prov.WW, PCS_CCL_THREADS);
   PCS_LAUNCH("k_ccl_area", st, k_ccl_area<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, ws.aux, B));
   PCS_LAUNCH("k_ccl_mark_small", st, k_ccl_mark_small<<<gw, PCS_CCL_THREADS, 0, st>>>(ws.parent, ws.rootbits, ws.aux, min_size, B, H, prov.WW));
-  PCS_LAUNCH("k_ccl_select", st, k_ccl_select<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, 0, nullptr, nullptr, out, B));
+  PCS_LAUNCH("k_ccl_select", st, k_ccl_select<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, 0, nullptr, nullptr, out, nullptr, B));
   return pcs_check_launch("remove small objects");
 }
 
@@ -726,7 +825,7 @@ int pcs_select_components_bits(const uint32_t* bits, const uint32_t* seeds, uint
   if (rc) return rc;
   unsigned gw = pcs_blocks((long long)B * H * prov.WW, PCS_CCL_THREADS);
   PCS_LAUNCH("k_ccl_mark", st, k_ccl_mark<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, seeds, 1, B));
-  PCS_LAUNCH("k_ccl_select", st, k_ccl_select<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, 1, nullptr, nullptr, out, B));
+  PCS_LAUNCH("k_ccl_select", st, k_ccl_select<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, 1, nullptr, nullptr, out, nullptr, B));
   return pcs_check_launch("select components");
 }
 
@@ -746,7 +845,7 @@ int pcs_local_maxima_conn(const uint32_t* planes, const uint32_t* higher, uint32
   unsigned gw = pcs_blocks((long long)B * H * prov.WW, PCS_CCL_THREADS);
   PCS_LAUNCH("k_ccl_mark", st, k_ccl_mark<PcsGenProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, higher, 1, B));
   // a plateau that is the whole image (counts == 1) is not a maximum
-  PCS_LAUNCH("k_ccl_select", st, k_ccl_select<PcsGenProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, 0, nullptr, counts, out, B));
+  PCS_LAUNCH("k_ccl_select", st, k_ccl_select<PcsGenProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, 0, nullptr, counts, out, nullptr, B));
   return pcs_check_launch("local maxima");
 }
 

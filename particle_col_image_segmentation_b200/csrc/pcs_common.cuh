@@ -77,3 +77,24 @@ __device__ __forceinline__ int pcs_warp_excl_scan(int v, int lane, int* total) {
   *total = __shfl_sync(0xffffffffu, x, 31);
   return x - v;
 }
+
+// 32 mask bits -> 32 bytes (0/1) with two 16-byte stores when the row allows it
+__device__ __forceinline__ void pcs_store_mask_bytes(uint8_t* __restrict__ row, int k, int W, uint32_t w) {
+  const int x0 = k << 5;
+  if (x0 + 32 <= W && ((((uintptr_t)(row + x0)) & 15) == 0)) {
+    uint32_t o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      uint32_t n = (w >> (4 * i)) & 0xfu;
+      // spread 4 bits to 4 bytes
+      o[i] = (n & 1u) | ((n & 2u) << 7) | ((n & 4u) << 14) | ((n & 8u) << 21);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(row + x0);
+    dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  } else {
+    int n = min(32, W - x0);
+    for (int i = 0; i < n; ++i) row[x0 + i] = (w >> i) & 1u;
+  }
+}
+

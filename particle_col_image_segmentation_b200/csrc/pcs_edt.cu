@@ -145,8 +145,20 @@ __device__ __forceinline__ uint32_t edt_vdist(uint32_t z, int r, uint32_t cu, ui
   return min(gu, gd);
 }
 
+// sqrt of the squared distances the near phase can produce (<= EDT_DMAX^2): one L1-resident load
+// instead of a 45-instruction fp64 sqrt per foreground pixel; filled on the device with the same
+// IEEE sqrt the far phase uses, so both phases round identically.
+#define EDT_LUT_N (EDT_DMAX * EDT_DMAX + 1)
+__device__ double g_edt_sqrt_lut[EDT_LUT_N];
+__global__ void k_edt_lut_init() {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (int)EDT_LUT_N) g_edt_sqrt_lut[i] = sqrt((double)i);
+}
+
 // Phase 1: CTA per (column tile, band, slice).  Every pixel whose vertical distance is at most
 // EDT_DMAX is final after an outward search inside the tile + halo; the others flag their row.
+// Background pixels (the vast majority) are written by vectorised zero stores; only foreground
+// pixels are visited individually, column by column off the vertical bit words.
 #define EDT_TW 256
 #define EDT_HALO 40
 #define EDT_TWH (EDT_TW + 2 * EDT_HALO)
@@ -155,15 +167,46 @@ __global__ void __launch_bounds__(EDT_TW)
                double* __restrict__ dist, int32_t* __restrict__ sq, uint32_t* __restrict__ thr_bits, int thr_sq,
                uint8_t* __restrict__ row_far, int H, int W, int WW, int NB) {
   __shared__ uint16_t g[32][EDT_TWH];
+  __shared__ uint32_t tb[32][EDT_TW / 32];
   const int tid = threadIdx.x;
   const int Wp = WW << 5;
   const int x0 = blockIdx.x * EDT_TW;
   const int q = blockIdx.y;
   const long long b = blockIdx.z;
   const long long band = (b * NB + q) * (long long)Wp;
+  const int rows = min(32, H - (q << 5));
+  const int cols = min(EDT_TW, W - x0);
   // background pixels have g = 0: clear the tile, then visit only the foreground rows of each column
   uint32_t* gz = reinterpret_cast<uint32_t*>(&g[0][0]);
   for (int i = tid; i < 32 * EDT_TWH / 2; i += EDT_TW) gz[i] = 0u;
+  // zero the outputs of the whole tile with 16-byte stores
+  const long long obase = (b * H + (q << 5)) * (long long)W + x0;
+  if (dist) {
+    if (cols == EDT_TW && (W & 1) == 0) {
+      for (int i = tid; i < rows * (EDT_TW / 2); i += EDT_TW) {
+        const int r = i / (EDT_TW / 2), c = (i % (EDT_TW / 2)) * 2;
+        *reinterpret_cast<double2*>(dist + obase + (long long)r * W + c) = make_double2(0.0, 0.0);
+      }
+    } else {
+      for (int i = tid; i < rows * EDT_TW; i += EDT_TW) {
+        const int r = i / EDT_TW, c = i % EDT_TW;
+        if (c < cols) dist[obase + (long long)r * W + c] = 0.0;
+      }
+    }
+  }
+  if (sq) {
+    if (cols == EDT_TW && (W & 3) == 0) {
+      for (int i = tid; i < rows * (EDT_TW / 4); i += EDT_TW) {
+        const int r = i / (EDT_TW / 4), c = (i % (EDT_TW / 4)) * 4;
+        *reinterpret_cast<int4*>(sq + obase + (long long)r * W + c) = make_int4(0, 0, 0, 0);
+      }
+    } else {
+      for (int i = tid; i < rows * EDT_TW; i += EDT_TW) {
+        const int r = i / EDT_TW, c = i % EDT_TW;
+        if (c < cols) sq[obase + (long long)r * W + c] = 0;
+      }
+    }
+  }
   __syncthreads();
   for (int col = tid; col < EDT_TWH; col += EDT_TW) {
     const int x = x0 - EDT_HALO + col;
@@ -186,45 +229,45 @@ __global__ void __launch_bounds__(EDT_TW)
   __syncthreads();
   const int x = x0 + tid;
   const int col = tid + EDT_HALO;
-  const int rows = min(32, H - (q << 5));
-  for (int r = 0; r < rows; ++r) {
-    const int y = (q << 5) + r;
-    const uint32_t gx = x < W ? g[r][col] : 0u;
-    const long long o = (b * H + y) * (long long)W + x;
-    if (!__any_sync(0xffffffffu, gx != 0u)) {
-      // 32 background pixels in a row (the common case): plain zero stores
-      if (x < W) {
-        if (dist) dist[o] = 0.0;
-        if (sq) sq[o] = 0;
-      }
-      if (thr_bits && (tid & 31) == 0 && (x >> 5) < WW)
-        thr_bits[(b * H + y) * (long long)WW + (x >> 5)] = thr_sq >= 0 ? pcs_valid_mask(x >> 5, W) : 0u;
-      continue;
+  if (thr_bits) {
+    // background pixels are at distance 0: start every row word from them (warp w owns word w)
+    for (int r = 0; r < 32; ++r) {
+      unsigned bg = __ballot_sync(0xffffffffu, x < W && g[r][col] == 0u);
+      if ((tid & 31) == 0) tb[r][tid >> 5] = thr_sq >= 0 ? bg : 0u;
     }
-    uint32_t d2 = 0;
-    bool far = false;
-    if (x < W) {
+    __syncthreads();
+  }
+  if (x < W) {
+    uint32_t f = __ldg(vw + band + x);
+    if (rows < 32) f &= (1u << rows) - 1u;
+    while (f) {
+      const int r = __ffs(f) - 1;
+      f &= f - 1;
+      const uint32_t gx = g[r][col];
+      const int y = (q << 5) + r;
       if (gx > EDT_DMAX) {
-        far = true;
-      } else if (gx != 0u) {
-        uint32_t best = gx * gx;
-        for (uint32_t dd = 1; dd * dd < best; ++dd) {  // dd < gx <= EDT_HALO: stays inside the tile + halo
-          const uint32_t d2d = dd * dd;
-          const uint32_t g1 = g[r][col - (int)dd], g2 = g[r][col + (int)dd];
-          if (g1 != EDT_INF) best = min(best, d2d + g1 * g1);
-          if (g2 != EDT_INF) best = min(best, d2d + g2 * g2);
-        }
-        d2 = best;
+        row_far[b * H + y] = 1;  // solved by k_edt_far
+        continue;
       }
-      if (!far) {
-        if (dist) dist[o] = sqrt((double)d2);
-        if (sq) sq[o] = (int32_t)d2;
+      uint32_t best = gx * gx;
+      for (uint32_t dd = 1; dd * dd < best; ++dd) {  // dd < gx <= EDT_HALO: stays inside the tile + halo
+        const uint32_t d2d = dd * dd;
+        const uint32_t g1 = g[r][col - (int)dd], g2 = g[r][col + (int)dd];
+        if (g1 != EDT_INF) best = min(best, d2d + g1 * g1);
+        if (g2 != EDT_INF) best = min(best, d2d + g2 * g2);
       }
+      const long long o = (b * H + y) * (long long)W + x;
+      if (dist) dist[o] = g_edt_sqrt_lut[best];
+      if (sq) sq[o] = (int32_t)best;
+      if (thr_bits && (int)best <= thr_sq) atomicOr(&tb[r][tid >> 5], 1u << (tid & 31));
     }
-    if (__any_sync(0xffffffffu, far) && (tid & 31) == 0) row_far[b * H + y] = 1;
-    if (thr_bits) {
-      unsigned ball = __ballot_sync(0xffffffffu, x < W && !far && (int)d2 <= thr_sq);
-      if ((tid & 31) == 0 && (x >> 5) < WW) thr_bits[(b * H + y) * (long long)WW + (x >> 5)] = ball;
+  }
+  if (thr_bits) {
+    __syncthreads();
+    for (int i = tid; i < rows * (EDT_TW / 32); i += EDT_TW) {
+      const int r = i / (EDT_TW / 32), w = i % (EDT_TW / 32);
+      const int kw = (x0 >> 5) + w;
+      if (kw < WW) thr_bits[(b * H + (q << 5) + r) * (long long)WW + kw] = tb[r][w];
     }
   }
 }
@@ -316,6 +359,15 @@ int pcs_edt_bits(const uint32_t* bits, int invert, int B, int H, int W, double* 
              k_edt_transpose<<<pcs_blocks((long long)B * NB * WW * 32, 256), 256, 0, st>>>(bits, invert, vw, B, H, W, WW, NB));
   dim3 gc((W + 127) / 128, B);
   PCS_LAUNCH("k_edt_carry", st, k_edt_carry<<<gc, 128, 0, st>>>(vw, up, dn, W, Wp, NB));
+  {
+    static bool lut_ready[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !lut_ready[dev]) {
+      PCS_LAUNCH("k_edt_lut_init", st, k_edt_lut_init<<<(EDT_LUT_N + 255) / 256, 256, 0, st>>>());
+      lut_ready[dev] = true;
+    }
+  }
   dim3 gn((W + EDT_TW - 1) / EDT_TW, NB, B);
   PCS_LAUNCH("k_edt_near", st,
              k_edt_near<<<gn, EDT_TW, 0, st>>>(vw, up, dn, dist, sq, thr_bits, thr_sq, row_far, H, W, WW, NB));

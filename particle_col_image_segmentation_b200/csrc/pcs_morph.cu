@@ -136,7 +136,8 @@ __device__ __forceinline__ void pcs_add5(uint32_t a, uint32_t b, uint32_t c, uin
 }
 
 __global__ void __launch_bounds__(MORPH_THREADS)
-    k_majority5_bits(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int B, int H, int W, int WW) {
+    k_majority5_bits(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint8_t* __restrict__ mask, int B, int H, int W,
+                     int WW) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)B * H * WW;
   if (t >= total) return;
@@ -164,8 +165,9 @@ __global__ void __launch_bounds__(MORPH_THREADS)
   const uint32_t s3 = t3 ^ n2, n3 = t3 & n2;
   const uint32_t s4 = c4 ^ m3 ^ n3;
   // median is 1 when at least 13 of the 25 are set: total >= 13
-  const uint32_t ge13 = s4 | (s3 & s2 & (s1 | s0));
-  out[t] = ge13 & pcs_valid_mask(k, W);
+  const uint32_t ge13 = (s4 | (s3 & s2 & (s1 | s0))) & pcs_valid_mask(k, W);
+  out[t] = ge13;
+  if (mask) pcs_store_mask_bytes(mask + (b * H + y) * (long long)W, k, W, ge13);  // fused uint8 output
 }
 
 // generic uint8 median, size in {3, 5, 7}, mode reflect; CTA tile 32 x 8 with halo in shared memory
@@ -218,6 +220,10 @@ int pcs_dilate_bits(const uint32_t* in, uint32_t* out, const int32_t* runs, int 
 }
 
 int pcs_majority_bits(const uint32_t* in, uint32_t* out, int size, int B, int H, int W, void* stream) {
+  return pcs_majority_bits_mask(in, out, nullptr, size, B, H, W, stream);
+}
+
+int pcs_majority_bits_mask(const uint32_t* in, uint32_t* out, uint8_t* mask, int size, int B, int H, int W, void* stream) {
   PCS_REQUIRE(B >= 1 && H >= 1 && W >= 1, "empty batch or image");
   PCS_REQUIRE(size == 3 || size == 5 || size == 7, "median size must be 3, 5 or 7");
   PCS_REQUIRE(H >= size && W >= size, "image smaller than the median window");
@@ -228,9 +234,10 @@ int pcs_majority_bits(const uint32_t* in, uint32_t* out, int size, int B, int H,
   if (size == 3)
     PCS_LAUNCH("k_majority_bits", st, k_majority_bits<3><<<g, MORPH_THREADS, 0, st>>>(in, out, B, H, W, WW));
   else if (size == 5)
-    PCS_LAUNCH("k_majority5_bits", st, k_majority5_bits<<<g, MORPH_THREADS, 0, st>>>(in, out, B, H, W, WW));
+    PCS_LAUNCH("k_majority5_bits", st, k_majority5_bits<<<g, MORPH_THREADS, 0, st>>>(in, out, mask, B, H, W, WW));
   else
     PCS_LAUNCH("k_majority_bits", st, k_majority_bits<7><<<g, MORPH_THREADS, 0, st>>>(in, out, B, H, W, WW));
+  if (mask && size != 5) return pcs_unpack_bits(out, mask, B, H, W, stream);
   return pcs_check_launch("majority");
 }
 

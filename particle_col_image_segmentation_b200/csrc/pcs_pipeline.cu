@@ -33,7 +33,7 @@ size_t seg_carve(void* ws, int B, int H, int W, SegWs* out) {
   w.bits = (uint32_t*)take(bits_bytes);
   w.keep = (uint32_t*)take(bits_bytes);
   w.refined = (uint32_t*)take(bits_bytes);
-  w.ccl_bytes = pcs_ccl_workspace_bytes(B, H, W, 0);
+  w.ccl_bytes = pcs_fill_holes_table_workspace_bytes(B, H, W);  // covers the labelling pass too
   w.ccl = take(w.ccl_bytes);
   w.edt_bytes = pcs_edt_workspace_bytes(B, H, W);
   w.edt = take(w.edt_bytes);
@@ -65,10 +65,11 @@ int pcs_segment_chunk(const uint16_t* img, int B, int H, int W, int denoise_size
   const uint32_t* bits = w.raw;
   STEP(pcs_compare_u16(img, 0, thr, 0, w.raw, nullptr, B, H, W, stream));
   if (denoise_size > 1) {
-    STEP(pcs_majority_bits(w.raw, w.bits, denoise_size, B, H, W, stream));
+    STEP(pcs_majority_bits_mask(w.raw, w.bits, mask, denoise_size, B, H, W, stream));  // bits + uint8 mask in one pass
     bits = w.bits;
+  } else {
+    STEP(pcs_unpack_bits(bits, mask, B, H, W, stream));
   }
-  STEP(pcs_unpack_bits(bits, mask, B, H, W, stream));
   STEP(pcs_label_bits(bits, B, H, W, 8, 0, labels, 4, counts, offsets, nullptr, 0, w.ccl, w.ccl_bytes, stream));
   STEP(pcs_table_init(table, cap, stream));
   STEP(pcs_region_table(labels, 4, img, 1, bits, nullptr, offsets, table, cap, B, H, W, stream));
@@ -77,8 +78,8 @@ int pcs_segment_chunk(const uint16_t* img, int B, int H, int W, int denoise_size
     STEP(pcs_select_by_area(labels, bits, table, cap, offsets, min_size, w.keep, B, H, W, stream));
     kept = w.keep;
   }
-  STEP(pcs_fill_holes_bits(kept, w.refined, B, H, W, w.ccl, w.ccl_bytes, stream));
-  STEP(pcs_unpack_bits(w.refined, refined, B, H, W, stream));
+  // holes of the kept components lie inside their bounding boxes (from the table just built)
+  STEP(pcs_fill_holes_table_bits(kept, table, cap, offsets, min_size > 1 ? min_size : 1, w.refined, refined, B, H, W, w.ccl, w.ccl_bytes, stream));
   STEP(pcs_edt_bits(w.refined, 0, B, H, W, edt, nullptr, nullptr, 0, w.edt, w.edt_bytes, stream));
 #undef STEP
   return PCS_OK;

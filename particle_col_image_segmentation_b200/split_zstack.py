@@ -93,49 +93,79 @@ class SegmentResult:
         }
 
 
+class SegmentPlan:
+    """The pipeline bound to fixed device buffers, optionally captured in a CUDA graph.
+
+    One ``pcs_segment_chunk`` call per chunk of slices is enqueued on the current stream; with
+    ``graph=True`` the calls are captured once and replayed, which removes the launch gaps
+    between the ~34 kernels of a chunk (a z-stack is many small 2-D problems, so launch
+    latency matters).  ``plan()`` is asynchronous and returns the bound ``SegmentResult``.
+    """
+
+    def __init__(self, stack, denoise_size=5, min_size=20, chunk=16, max_regions_per_slice=1 << 14, out=None, z0=0, graph=False):
+        ops.require_cuda(stack, "stack")
+        if stack.dtype != torch.uint16 or stack.dim() != 3:
+            raise _lib.PcsError(f"segment pipeline expects a (Z, H, W) uint16 tensor, got {tuple(stack.shape)} {stack.dtype}")
+        self.stack = stack
+        Z, H, W = (int(v) for v in stack.shape)
+        dev = stack.device
+        if out is None:
+            out = SegmentResult(
+                mask=torch.empty((Z, H, W), dtype=torch.uint8, device=dev),
+                labels=torch.empty((Z, H, W), dtype=torch.int32, device=dev),
+                refined=torch.empty((Z, H, W), dtype=torch.uint8, device=dev),
+                edt=torch.empty((Z, H, W), dtype=torch.float64, device=dev),
+                threshold=torch.empty(Z, dtype=torch.int32, device=dev),
+                counts=torch.empty(Z, dtype=torch.int32, device=dev),
+            )
+        self.out = out
+        out.z0 = z0
+        self.dn, self.ms = int(denoise_size or 0), int(min_size or 0)
+        self.lib = _lib.load()
+        chunk = max(1, min(int(chunk), Z))
+        out.tables = []
+        self.calls = []
+        nws = self.lib.pcs_segment_workspace_bytes(chunk, H, W)
+        self.ws = torch.empty(nws, dtype=torch.uint8, device=dev)  # owned: graph replays need stable pointers
+        for a in range(0, Z, chunk):
+            b = min(Z, a + chunk)
+            B = b - a
+            offsets = torch.empty(B + 1, dtype=torch.int32, device=dev)
+            cap = int(max_regions_per_slice) * B
+            table = torch.empty((ops.TABLE_COLS, cap), dtype=torch.int64, device=dev)
+            out.tables.append((a, offsets, table))
+            P = ops._p
+            self.calls.append((P(stack[a:b]), B, H, W, self.dn, self.ms, P(out.mask[a:b]), P(out.labels[a:b]), P(out.refined[a:b]), P(out.edt[a:b]),
+                               P(out.threshold[a:b]), P(out.counts[a:b]), P(offsets), P(table), cap, P(self.ws), nws))
+        self.graph = None
+        if graph:
+            self._enqueue()  # warm-up: one-time initialisations must not land in the capture
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue()
+            self.graph = g
+
+    def _enqueue(self):
+        st = ops._stream()
+        for c in self.calls:
+            _lib.check(self.lib.pcs_segment_chunk(*c, st), "pcs_segment_chunk")
+
+    def __call__(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._enqueue()
+        return self.out
+
+
 def segment_zstack_device(stack, denoise_size=5, min_size=20, chunk=16, max_regions_per_slice=1 << 14, out=None, z0=0):
     """Full pipeline over a device-resident ``(Z, H, W)`` uint16 stack.
 
     Asynchronous on the current stream; no host synchronisation inside.  ``out`` may
     carry preallocated output tensors (a previous ``SegmentResult``) to reuse.
     """
-    ops.require_cuda(stack, "stack")
-    if stack.dtype != torch.uint16 or stack.dim() != 3:
-        raise _lib.PcsError(f"segment_zstack_device expects a (Z, H, W) uint16 tensor, got {tuple(stack.shape)} {stack.dtype}")
-    Z, H, W = (int(s) for s in stack.shape)
-    dev = stack.device
-    if out is None:
-        out = SegmentResult(
-            mask=torch.empty((Z, H, W), dtype=torch.uint8, device=dev),
-            labels=torch.empty((Z, H, W), dtype=torch.int32, device=dev),
-            refined=torch.empty((Z, H, W), dtype=torch.uint8, device=dev),
-            edt=torch.empty((Z, H, W), dtype=torch.float64, device=dev),
-            threshold=torch.empty(Z, dtype=torch.int32, device=dev),
-            counts=torch.empty(Z, dtype=torch.int32, device=dev),
-        )
-    out.tables = []
-    out.z0 = z0
-    lib = _lib.load()
-    st = ops._stream()
-    P = ops._p
-    dn = int(denoise_size or 0)
-    ms = int(min_size or 0)
-    for a in range(0, Z, chunk):
-        b = min(Z, a + chunk)
-        B = b - a
-        offsets = torch.empty(B + 1, dtype=torch.int32, device=dev)
-        cap = max_regions_per_slice * B
-        table = torch.empty((ops.TABLE_COLS, cap), dtype=torch.int64, device=dev)
-        nws = lib.pcs_segment_workspace_bytes(B, H, W)
-        ws = ops._ws(nws, dev, "segment")
-        # one C-ABI call per chunk: histogram + Otsu, threshold, median, labels, table, refine, EDT
-        _lib.check(
-            lib.pcs_segment_chunk(P(stack[a:b]), B, H, W, dn, ms, P(out.mask[a:b]), P(out.labels[a:b]), P(out.refined[a:b]), P(out.edt[a:b]),
-                                  P(out.threshold[a:b]), P(out.counts[a:b]), P(offsets), P(table), cap, P(ws), nws, st),
-            "pcs_segment_chunk",
-        )
-        out.tables.append((a, offsets, table))
-    return out
+    return SegmentPlan(stack, denoise_size, min_size, chunk, max_regions_per_slice, out=out, z0=z0)()
 
 
 def segment_zstack(stack, denoise_size=5, min_size=20, chunk=16, max_regions_per_slice=1 << 14, z0=0):
@@ -174,18 +204,19 @@ def alloc_host_outputs(Z, H, W):
 
 def segment_zstack_pinned(host_in, host_out, denoise_size=5, min_size=20, chunk=16, max_regions_per_slice=1 << 14):
     """Host buffers in, host buffers out: H2D copy of the stack, the device pipeline, D2H copy
-    of all five outputs and the table.  Device buffers are cached between calls.
-    Returns the number of table rows (``host_out['table']`` holds them)."""
+    of all five outputs and the table.  Device buffers and the captured pipeline are cached
+    between calls.  Returns the number of table rows (``host_out['table']`` holds them)."""
     dev = _io.device()
-    key = (str(dev), tuple(host_in.shape))
+    key = (str(dev), tuple(host_in.shape), denoise_size, min_size, chunk, max_regions_per_slice)
     st = _E2E_CACHE.get(key)
     if st is None:
-        st = {"in": torch.empty(tuple(host_in.shape), dtype=torch.uint16, device=dev), "res": None}
+        d_in = torch.empty(tuple(host_in.shape), dtype=torch.uint16, device=dev)
+        d_in.copy_(host_in)
+        st = {"in": d_in, "plan": SegmentPlan(d_in, denoise_size, min_size, chunk, max_regions_per_slice, graph=True)}
         _E2E_CACHE.clear()
         _E2E_CACHE[key] = st
     st["in"].copy_(host_in, non_blocking=True)
-    res = segment_zstack_device(st["in"], denoise_size, min_size, chunk, max_regions_per_slice, out=st["res"])
-    st["res"] = res
+    res = st["plan"]()
     for k in ("mask", "labels", "refined", "edt", "threshold", "counts"):
         host_out[k].copy_(getattr(res, k), non_blocking=True)
     table = res.table_device()
