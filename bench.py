@@ -245,7 +245,8 @@ def run_b200(args):
     # parity spot check against the oracle on one slice of this very stack (outside the timed region)
     parity = None
     if rank == 0:
-        r, table = step()
+        r = plan()  # local only: no collective may run on a single rank
+        table = r.table_device()
         torch.cuda.synchronize()
         zi = Z // 2
         want = opipe.segment_slice(stack[zi].cpu().numpy(), z=zi)
