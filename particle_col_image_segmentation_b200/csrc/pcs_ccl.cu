@@ -466,13 +466,33 @@ __global__ void __launch_bounds__(PCS_CCL_THREADS)
   __syncwarp();
   OutT* orow = out + (b * H + y) * (long long)W;
   int nk = min(32, WW - ch * 32);
-  for (int kk = 0; kk < nk; ++kk) {
-    uint32_t f = __shfl_sync(0xffffffffu, F, kk);
-    uint32_t s = __shfl_sync(0xffffffffu, S, kk);
-    int x = ((ch * 32 + kk) << 5) + lane;
-    int v = 0;
-    if ((f >> lane) & 1u) v = lab[wl][kk][pcs_start_at_or_below(s, lane)];
-    if (x < W) orow[x] = (OutT)v;
+  if (sizeof(OutT) == 4 && (W & 3) == 0) {
+    // 16-byte stores: a lane owns 4 consecutive pixels, 4 words (128 pixels) per iteration
+    const int sub = lane >> 3, nib = (lane & 7) << 2;
+    for (int k4 = 0; k4 < nk; k4 += 4) {
+      const int kk = k4 + sub;
+      uint32_t f = __shfl_sync(0xffffffffu, F, kk & 31);
+      uint32_t s = __shfl_sync(0xffffffffu, S, kk & 31);
+      int4 v = make_int4(0, 0, 0, 0);
+      const uint32_t n = kk < nk ? (f >> nib) & 0xfu : 0u;
+      if (n) {
+        if (n & 1u) v.x = lab[wl][kk][pcs_start_at_or_below(s, nib)];
+        if (n & 2u) v.y = lab[wl][kk][pcs_start_at_or_below(s, nib + 1)];
+        if (n & 4u) v.z = lab[wl][kk][pcs_start_at_or_below(s, nib + 2)];
+        if (n & 8u) v.w = lab[wl][kk][pcs_start_at_or_below(s, nib + 3)];
+      }
+      const int x = ((ch * 32 + kk) << 5) + nib;
+      if (kk < nk && x < W) *reinterpret_cast<int4*>(orow + x) = v;  // W % 4 == 0: x + 3 < W too
+    }
+  } else {
+    for (int kk = 0; kk < nk; ++kk) {
+      uint32_t f = __shfl_sync(0xffffffffu, F, kk);
+      uint32_t s = __shfl_sync(0xffffffffu, S, kk);
+      int x = ((ch * 32 + kk) << 5) + lane;
+      int v = 0;
+      if ((f >> lane) & 1u) v = lab[wl][kk][pcs_start_at_or_below(s, lane)];
+      if (x < W) orow[x] = (OutT)v;
+    }
   }
 }
 

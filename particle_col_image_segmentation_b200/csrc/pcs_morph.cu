@@ -135,39 +135,50 @@ __device__ __forceinline__ void pcs_add5(uint32_t a, uint32_t b, uint32_t c, uin
   s2 = m1 & m2;
 }
 
+#define MAJ_ROWS 8  // output rows per thread: each input row's horizontal sums are computed once and reused 5 times
 __global__ void __launch_bounds__(MORPH_THREADS)
     k_majority5_bits(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint8_t* __restrict__ mask, int B, int H, int W,
-                     int WW) {
+                     int WW, int strips) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)B * H * WW;
+  long long total = (long long)B * strips * WW;
   if (t >= total) return;
   const int k = (int)(t % WW);
-  const int y = (int)((t / WW) % H);
-  const long long b = t / ((long long)WW * H);
+  const int strip = (int)((t / WW) % strips);
+  const long long b = t / ((long long)WW * strips);
   const uint32_t* src = in + b * (long long)H * WW;
-  uint32_t r0[5], r1[5], r2[5];  // per row: bit-sliced count of the 5 horizontal neighbours
+  const int y0 = strip * MAJ_ROWS;
+  const uint32_t vm = pcs_valid_mask(k, W);
+  uint32_t r0[5], r1[5], r2[5];  // sliding window: bit-sliced count of the 5 horizontal neighbours per input row
 #pragma unroll
-  for (int dy = -2; dy <= 2; ++dy) {
-    const unsigned long long win = pcs_window_reflect(src + (long long)pcs_reflect(y + dy, H) * WW, k, W, WW, 2);
-    pcs_add5((uint32_t)(win >> 14), (uint32_t)(win >> 15), (uint32_t)(win >> 16), (uint32_t)(win >> 17), (uint32_t)(win >> 18),
-             r0[dy + 2], r1[dy + 2], r2[dy + 2]);
+  for (int i = 0; i < MAJ_ROWS + 4; ++i) {
+    const int yi = y0 - 2 + i;  // input row entering the window
+    if (yi - 2 < H) {           // still needed by some output row of the image
+      const unsigned long long win = pcs_window_reflect(src + (long long)pcs_reflect(yi, H) * WW, k, W, WW, 2);
+      pcs_add5((uint32_t)(win >> 14), (uint32_t)(win >> 15), (uint32_t)(win >> 16), (uint32_t)(win >> 17), (uint32_t)(win >> 18),
+               r0[i % 5], r1[i % 5], r2[i % 5]);
+    }
+    if (i >= 4) {
+      const int y = y0 + i - 4;  // output row whose 5 input rows are now in the window
+      if (y < H) {
+        uint32_t a0, a1, a2, b1, b2, b3, c2, c3, c4;
+        pcs_add5(r0[0], r0[1], r0[2], r0[3], r0[4], a0, a1, a2);  // ones   (weight 1)
+        pcs_add5(r1[0], r1[1], r1[2], r1[3], r1[4], b1, b2, b3);  // twos   (weight 2)
+        pcs_add5(r2[0], r2[1], r2[2], r2[3], r2[4], c2, c3, c4);  // fours  (weight 4)
+        // total = A + 2B + 4C, bit by bit
+        const uint32_t s0 = a0;
+        const uint32_t s1 = a1 ^ b1, k2 = a1 & b1;
+        const uint32_t t2 = a2 ^ b2 ^ c2, m2 = (a2 & b2) | (c2 & (a2 ^ b2));
+        const uint32_t s2 = t2 ^ k2, n2 = t2 & k2;
+        const uint32_t t3 = b3 ^ c3 ^ m2, m3 = (b3 & c3) | (m2 & (b3 ^ c3));
+        const uint32_t s3 = t3 ^ n2, n3 = t3 & n2;
+        const uint32_t s4 = c4 ^ m3 ^ n3;
+        // median is 1 when at least 13 of the 25 are set: total >= 13
+        const uint32_t ge13 = (s4 | (s3 & s2 & (s1 | s0))) & vm;
+        out[(b * H + y) * (long long)WW + k] = ge13;
+        if (mask) pcs_store_mask_bytes(mask + (b * H + y) * (long long)W, k, W, ge13);  // fused uint8 output
+      }
+    }
   }
-  uint32_t a0, a1, a2, b1, b2, b3, c2, c3, c4;
-  pcs_add5(r0[0], r0[1], r0[2], r0[3], r0[4], a0, a1, a2);  // ones   (weight 1)
-  pcs_add5(r1[0], r1[1], r1[2], r1[3], r1[4], b1, b2, b3);  // twos   (weight 2)
-  pcs_add5(r2[0], r2[1], r2[2], r2[3], r2[4], c2, c3, c4);  // fours  (weight 4)
-  // total = A + 2B + 4C, bit by bit
-  const uint32_t s0 = a0;
-  const uint32_t s1 = a1 ^ b1, k2 = a1 & b1;
-  const uint32_t t2 = a2 ^ b2 ^ c2, m2 = (a2 & b2) | (c2 & (a2 ^ b2));
-  const uint32_t s2 = t2 ^ k2, n2 = t2 & k2;
-  const uint32_t t3 = b3 ^ c3 ^ m2, m3 = (b3 & c3) | (m2 & (b3 ^ c3));
-  const uint32_t s3 = t3 ^ n2, n3 = t3 & n2;
-  const uint32_t s4 = c4 ^ m3 ^ n3;
-  // median is 1 when at least 13 of the 25 are set: total >= 13
-  const uint32_t ge13 = (s4 | (s3 & s2 & (s1 | s0))) & pcs_valid_mask(k, W);
-  out[t] = ge13;
-  if (mask) pcs_store_mask_bytes(mask + (b * H + y) * (long long)W, k, W, ge13);  // fused uint8 output
 }
 
 // generic uint8 median, size in {3, 5, 7}, mode reflect; CTA tile 32 x 8 with halo in shared memory
@@ -234,7 +245,11 @@ int pcs_majority_bits_mask(const uint32_t* in, uint32_t* out, uint8_t* mask, int
   if (size == 3)
     PCS_LAUNCH("k_majority_bits", st, k_majority_bits<3><<<g, MORPH_THREADS, 0, st>>>(in, out, B, H, W, WW));
   else if (size == 5)
-    PCS_LAUNCH("k_majority5_bits", st, k_majority5_bits<<<g, MORPH_THREADS, 0, st>>>(in, out, mask, B, H, W, WW));
+  {
+    const int strips = (H + MAJ_ROWS - 1) / MAJ_ROWS;
+    PCS_LAUNCH("k_majority5_bits", st,
+               k_majority5_bits<<<pcs_blocks((long long)B * strips * WW, MORPH_THREADS), MORPH_THREADS, 0, st>>>(in, out, mask, B, H, W, WW, strips));
+  }
   else
     PCS_LAUNCH("k_majority_bits", st, k_majority_bits<7><<<g, MORPH_THREADS, 0, st>>>(in, out, B, H, W, WW));
   if (mask && size != 5) return pcs_unpack_bits(out, mask, B, H, W, stream);

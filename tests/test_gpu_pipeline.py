@@ -73,3 +73,58 @@ def test_split_channels_layout(seg):
     planes2 = seg.split_channels(z2, (1, 2))
     assert list(planes2) == ["RFP", "GFP"] and np.array_equal(planes2["RFP"], z2[:, 0])
     assert seg.plane_name("img", 3, "GFP") == "img_z3_GFP.tif"
+
+
+def test_segment_plan_graph_replay_matches_eager(seg):
+    """The captured CUDA graph replays the same kernels: outputs must be identical, repeatedly."""
+    stack = synth.zstack_u16(6, 160, 288, seed=77)
+    d = torch.from_numpy(stack).cuda()
+    eager = seg.SegmentPlan(d, chunk=4)()
+    want = eager.to_numpy()
+    plan = seg.SegmentPlan(d, chunk=4, graph=True)
+    for _ in range(3):
+        got = plan().to_numpy()
+        for k in ("threshold", "mask", "labels", "refined", "edt", "table", "counts"):
+            assert np.array_equal(got[k], want[k]), k
+    check(want, opipe.segment_zstack(stack))
+
+
+def test_pinned_host_path(seg):
+    stack = synth.zstack_u16(3, 128, 160, seed=31)
+    host_in = torch.from_numpy(stack).pin_memory()
+    host_out = seg.alloc_host_outputs(*stack.shape)
+    for _ in range(2):
+        n = seg.segment_zstack_pinned(host_in, host_out, chunk=2)
+    want = opipe.segment_zstack(stack)
+    assert n == len(want["table"]) and np.array_equal(host_out["table"].numpy(), want["table"])
+    assert np.array_equal(host_out["labels"].numpy(), want["labels"]) and np.array_equal(host_out["edt"].numpy(), want["edt"])
+    assert np.array_equal(host_out["mask"].numpy().astype(bool), want["mask"]) and np.array_equal(host_out["refined"].numpy().astype(bool), want["refined"])
+
+
+def test_fill_holes_from_table_matches_scipy(seg):
+    """The bounding-box restricted hole filling the pipeline uses == scipy.ndimage.binary_fill_holes."""
+    from scipy import ndimage as ndi
+
+    from particle_col_image_segmentation_b200 import _lib, ops
+
+    rng = np.random.default_rng(5)
+    for shape, p in (((3, 70, 97), 0.55), ((2, 130, 257), 0.45), ((1, 64, 64), 0.8), ((2, 33, 65), 0.2)):
+        m = rng.random(shape) < p
+        m[0, 5:25, 5:30] = True
+        m[0, 10:20, 10:25] = False  # a hole with islands inside
+        m[0, 13:16, 14:18] = True
+        B, H, W = shape
+        bits = ops.pack(torch.from_numpy(m).cuda())
+        labels, counts, offsets = ops.label_bits(bits, W, connectivity=8)
+        table = ops.new_table(max(1, int(offsets[-1])), bits.device)
+        ops.region_table(labels, offsets, table, fg_bits=bits)
+        lib = _lib.load()
+        n = lib.pcs_fill_holes_table_workspace_bytes(B, H, W)
+        ws = torch.empty(n, dtype=torch.uint8, device=bits.device)
+        out = torch.empty_like(bits)
+        mask = torch.empty((B, H, W), dtype=torch.uint8, device=bits.device)
+        _lib.check(lib.pcs_fill_holes_table_bits(bits.data_ptr(), table.data_ptr(), table.shape[1], offsets.data_ptr(), 1, out.data_ptr(), mask.data_ptr(), B, H, W, ws.data_ptr(), n, ops._stream()))
+        got = ops.unpack(out, W, torch.bool).cpu().numpy()
+        for i in range(B):
+            assert np.array_equal(got[i], ndi.binary_fill_holes(m[i])), (shape, i)
+        assert np.array_equal(mask.cpu().numpy().astype(bool), got)
