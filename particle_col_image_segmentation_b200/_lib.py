@@ -11,7 +11,7 @@ import shutil
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint8, c_uint16, c_uint32, c_uint64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpcs.so")
+LIB_PATH = os.environ.get("PCS_LIB_PATH") or os.path.join(HERE, "libpcs.so")  # override: A/B builds while tuning
 
 
 class PcsError(RuntimeError):

@@ -7,6 +7,8 @@
 //   area filter on regions           tiff_analysis.py:769-773 (as skimage remove_small_objects)
 //   merged_image |= (labels == v)    tiff_analysis.py:878
 //   skimage.morphology.local_maxima  refine_boundaries.py:63
+#include <type_traits>
+
 #include "pcs_ccl.cuh"
 
 #include "pcs.h"
@@ -123,10 +125,13 @@ __global__ void __launch_bounds__(PCS_CCL_THREADS) k_ccl_merge(P prov, int* __re
 // the global index of its tile-local root.  Only adjacencies that cross a tile edge remain for
 // the global pass (k_ccl_merge_edges), so a component spanning the image costs a chain over
 // tiles, not over pixels or rows.
-// binary masks have at most 16 runs per 32-pixel word, multi-valued images up to 32: both tile shapes
-// (16 rows x 16 slots, 8 rows x 32 slots) use 32 KB of shared parents
-template <class P> struct PcsTile { static constexpr int TR = 16, LOG_SPW = 4; };
-template <> struct PcsTile<PcsGenProv> { static constexpr int TR = 8, LOG_SPW = 5; };
+// Tile shape: TR rows x TW words, handled by 128 threads whatever the shape -- after the staging
+// phase only the non-empty words carry work, so a small CTA keeps many tiles in flight per SM.
+// Binary masks have at most 16 runs per 32-pixel word, multi-valued images up to 32: both shapes
+// (32 x 8 words x 16 slots, 16 x 8 words x 32 slots) hold 16 KB of shared parents.
+#define CCL_TILE_THREADS 128
+template <class P> struct PcsTile { static constexpr int TR = 32, TW = 8, LOG_SPW = 4; };
+template <> struct PcsTile<PcsGenProv> { static constexpr int TR = 16, TW = 8, LOG_SPW = 5; };
 
 __device__ __forceinline__ int pcs_lfind(volatile int* sp, int n) {
   int r = n, p = sp[r];
@@ -154,54 +159,108 @@ __device__ __forceinline__ void pcs_lunion(int* sp, int a, int b) {
 }
 
 template <class P, int CONN>
-__global__ void __launch_bounds__(PcsTile<P>::TR * 32) k_ccl_tile(P prov, int* __restrict__ parent) {
-  constexpr int CCL_TR = PcsTile<P>::TR, LSPW = PcsTile<P>::LOG_SPW, SPW = 1 << LSPW;
-  __shared__ int sp[CCL_TR * 32 * SPW];
-  __shared__ uint32_t ssm[CCL_TR][32];
+__global__ void __launch_bounds__(CCL_TILE_THREADS) k_ccl_tile(P prov, int* __restrict__ parent) {
+  constexpr int TR = PcsTile<P>::TR, TW = PcsTile<P>::TW, LSPW = PcsTile<P>::LOG_SPW, SPW = 1 << LSPW, NWORDS = TR * TW;
+  constexpr bool kBin = std::is_same<P, PcsBinProv>::value;
+  __shared__ int sp[NWORDS * SPW];
+  __shared__ uint32_t fsm[NWORDS], ssm[NWORDS];
+  __shared__ uint32_t gsm[kBin ? 1 : 4][NWORDS];  // multi-valued: U, UL, UR, J planes of the tile
+  __shared__ unsigned short items[NWORDS];
+  __shared__ int nitems;
   const int H = prov.H, WW = prov.WW;
-  const int lane = threadIdx.x & 31, r = threadIdx.x >> 5;
-  const int k0 = blockIdx.x << 5, y0 = blockIdx.y * CCL_TR;
+  const int k0 = blockIdx.x * TW, y0 = blockIdx.y * TR;
   const long long b = blockIdx.z;
-  const int k = k0 + lane, y = y0 + r;
   P p = prov.slice(b);
-  PcsConnWords c;
-  c.F = c.S = 0;
-  const bool in = y < H && k < WW;
-  if (in) p.FS(y, k, c.F, c.S);
-  ssm[r][lane] = c.S;
-  const int sbase = (r * 32 + lane) << LSPW;
-  {
-    uint32_t S = c.S;
+  if (threadIdx.x == 0) nitems = 0;
+  __syncthreads();
+  // phase A, thread per word: stage the tile, give every run its own slot, list the non-empty words
+  for (int w = threadIdx.x; w < NWORDS; w += CCL_TILE_THREADS) {
+    const int r = w / TW, c = w % TW;
+    const int k = k0 + c, y = y0 + r;
+    uint32_t F = 0, S = 0;
+    if (y < H && k < WW) p.FS(y, k, F, S);
+    fsm[w] = F;
+    ssm[w] = S;
+    if (!kBin) {
+      PcsConnWords cw;
+      cw.U = cw.UL = cw.UR = 0;
+      cw.J = 0;
+      if (F) p.conn(y, k, cw);
+      gsm[0][w] = cw.U;
+      gsm[kBin ? 0 : 1][w] = cw.UL;
+      gsm[kBin ? 0 : 2][w] = cw.UR;
+      gsm[kBin ? 0 : 3][w] = (uint32_t)cw.J;
+    }
+    const int sbase = w << LSPW;
     int j = 0;
     while (S) {
       S &= S - 1;
       sp[sbase + j] = sbase + j;
       ++j;
     }
+    // one shared atomic per warp, not per word
+    const unsigned act = __activemask();
+    const unsigned has = __ballot_sync(act, F != 0u);
+    if (has) {
+      const int lane = threadIdx.x & 31;
+      const int leader = __ffs(has) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(&nitems, __popc(has));
+      base = __shfl_sync(act, base, leader);
+      if (F) items[base + __popc(has & ((1u << lane) - 1u))] = (unsigned short)w;
+    }
   }
   __syncthreads();
-  if (c.F) {
-    p.conn(y, k, c);
-    if (c.J && lane > 0) pcs_lunion(sp, sbase, sbase - SPW + __popc(ssm[r][lane - 1]) - 1);
-    if (r > 0 && (c.U | c.UL | c.UR)) {
-      uint32_t S = c.S;
+  const int n = nitems;
+  // phase B, thread per NON-EMPTY word (all lanes busy): unions between runs of this tile
+  for (int it = threadIdx.x; it < n; it += CCL_TILE_THREADS) {
+    const int w = items[it], wr = w / TW, wc = w % TW;
+    const uint32_t F = fsm[w];
+    uint32_t U = 0, UL = 0, UR = 0, Sa[3] = {0u, 0u, 0u};
+    int J;
+    if (kBin) {
+      const uint32_t fl = wc > 0 ? fsm[w - 1] : 0u;
+      J = (F & 1u) && (fl >> 31);
+      if (wr > 0) {
+        const uint32_t al = wc > 0 ? fsm[w - TW - 1] : 0u, ac = fsm[w - TW], ar = wc < TW - 1 ? fsm[w - TW + 1] : 0u;
+        U = F & ac;
+        UL = F & ((ac << 1) | (al >> 31));
+        UR = F & ((ac >> 1) | (ar << 31));
+      }
+    } else {
+      J = (int)gsm[kBin ? 0 : 3][w] && wc > 0;
+      if (wr > 0) {
+        U = gsm[0][w];
+        UL = gsm[kBin ? 0 : 1][w];
+        UR = gsm[kBin ? 0 : 2][w];
+      }
+    }
+    if (wr > 0) {
+      Sa[0] = wc > 0 ? ssm[w - TW - 1] : 0u;
+      Sa[1] = ssm[w - TW];
+      Sa[2] = wc < TW - 1 ? ssm[w - TW + 1] : 0u;
+    }
+    const int sbase = w << LSPW;
+    if (J) pcs_lunion(sp, sbase, sbase - SPW + __popc(ssm[w - 1]) - 1);
+    if (U | UL | UR) {
+      uint32_t S = ssm[w];
       int j = 0;
       while (S) {
         int s;
-        uint32_t R = pcs_pop_run(c.F, S, s);
-        unsigned long long T = ((unsigned long long)(c.U & R)) << 1;
-        if (CONN == 8) T |= (unsigned long long)(c.UL & R) | (((unsigned long long)(c.UR & R)) << 2);
+        uint32_t R = pcs_pop_run(F, S, s);
+        unsigned long long T = ((unsigned long long)(U & R)) << 1;
+        if (CONN == 8) T |= (unsigned long long)(UL & R) | (((unsigned long long)(UR & R)) << 2);
         while (T) {
           int i = __ffsll((long long)T) - 1;
           T &= T + (1ull << i);
           int rel = (i - 1) >> 5;
-          int ka = lane + rel;
-          if (ka >= 0 && ka < 32) {  // the run above lives in this tile
+          int ca = wc + rel;
+          if (ca >= 0 && ca < TW) {  // the run above lives in this tile
             int ja = (i - 1) & 31;
-            uint32_t Sa = c.Sa[rel + 1];
-            int sa = pcs_start_at_or_below(Sa, ja);
-            int ord = __popc(Sa & ((1u << sa) - 1u));
-            pcs_lunion(sp, sbase + j, (((r - 1) * 32 + ka) << LSPW) + ord);
+            uint32_t sa_w = Sa[rel + 1];
+            int sa = pcs_start_at_or_below(sa_w, ja);
+            int ord = __popc(sa_w & ((1u << sa) - 1u));
+            pcs_lunion(sp, sbase + j, ((w - TW + rel) << LSPW) + ord);
           }
         }
         ++j;
@@ -209,38 +268,55 @@ __global__ void __launch_bounds__(PcsTile<P>::TR * 32) k_ccl_tile(P prov, int* _
     }
   }
   __syncthreads();
-  if (c.S) {
-    const int Wp = WW << 5;
-    int* par = parent + b * (long long)H * Wp;
-    const int gbase = y * Wp + (k << 5);
-    uint32_t S = c.S;
+  // phase C, thread per non-empty word: every node points at the global index of its tile-local root
+  const int Wp = WW << 5;
+  int* par = parent + b * (long long)H * Wp;
+  for (int it = threadIdx.x; it < n; it += CCL_TILE_THREADS) {
+    const int w = items[it], wr = w / TW, wc = w % TW;
+    const int sbase = w << LSPW;
+    const int gbase = (y0 + wr) * Wp + ((k0 + wc) << 5);
+    uint32_t S = ssm[w];
     int j = 0;
     while (S) {
       int s = __ffs(S) - 1;
       S &= S - 1;
       int root = pcs_lfind(sp, sbase + j);
-      int rw = root >> LSPW, rj = root & (SPW - 1);  // word slot (row * 32 + lane) and run ordinal of the root
-      int rr = rw >> 5, rk = rw & 31;
-      int rs = __fns(ssm[rr][rk], 0, rj + 1);
-      par[gbase + s] = (y0 + rr) * Wp + ((k0 + rk) << 5) + rs;
+      int rw = root >> LSPW, rj = root & (SPW - 1);  // word of the root inside the tile, run ordinal
+      // start bit of the rj-th run of that word: clear the rj lowest start bits, take the next
+      uint32_t rsb = ssm[rw];
+      for (int q = 0; q < rj; ++q) rsb &= rsb - 1;
+      int rs = __ffs(rsb) - 1;
+      par[gbase + s] = (y0 + rw / TW) * Wp + ((k0 + rw % TW) << 5) + rs;
       ++j;
     }
   }
 }
 
-// thread per word: the unions k_ccl_tile could not do -- adjacencies across a tile edge
+// thread per TILE-EDGE word: the unions k_ccl_tile could not do -- adjacencies across a tile edge.
+// Edge words per slice: the top row of every tile (rows y % TR == 0, all words) followed by the
+// first / last word column of every tile in the remaining rows.
 template <class P, int CONN>
-__global__ void __launch_bounds__(PCS_CCL_THREADS) k_ccl_merge_edges(P prov, int* __restrict__ parent, int B) {
+__global__ void __launch_bounds__(PCS_CCL_THREADS) k_ccl_merge_edges(P prov, int* __restrict__ parent, int B, int per_slice) {
   const int H = prov.H, WW = prov.WW;
+  constexpr int CCL_TR = PcsTile<P>::TR, TW = PcsTile<P>::TW;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)B * H * WW;
-  if (t >= total) return;
-  int k = (int)(t % WW);
-  int y = (int)((t / WW) % H);
-  constexpr int CCL_TR = PcsTile<P>::TR;
-  const bool top = (y % CCL_TR) == 0, left = (k & 31) == 0, right = (k & 31) == 31;
-  if (!(top || left || right)) return;
-  long long b = t / ((long long)WW * H);
+  if (t >= (long long)B * per_slice) return;
+  const long long b = t / per_slice;
+  int e = (int)(t % per_slice);
+  const int ntop = (H + CCL_TR - 1) / CCL_TR;
+  int y, k;
+  if (e < ntop * WW) {
+    y = (e / WW) * CCL_TR;
+    k = e % WW;
+  } else {
+    e -= ntop * WW;
+    const int ncol = 2 * ((WW + TW - 1) / TW);  // first and last word of every tile column
+    const int rr = e / ncol, cc = e % ncol;      // rr counts the non-top rows
+    y = rr + rr / (CCL_TR - 1) + 1;              // skip rows that are multiples of TR
+    k = (cc >> 1) * TW + ((cc & 1) ? TW - 1 : 0);
+    if (y >= H || k >= WW) return;
+  }
+  const bool top = (y % CCL_TR) == 0, left = (k % TW) == 0, right = (k % TW) == TW - 1;
   P p = prov.slice(b);
   uint32_t F0, S0;
   p.FS(y, k, F0, S0);
@@ -690,15 +766,18 @@ static int ccl_forest(const P& prov, int B, int conn, const PcsCclWs& ws, int32_
   long long warps = (long long)B * H * CPR;
   unsigned gw = pcs_blocks(words, PCS_CCL_THREADS);
   unsigned gc = pcs_blocks(warps * 32, PCS_CCL_THREADS);
-  constexpr int CCL_TR = PcsTile<P>::TR;
+  constexpr int CCL_TR = PcsTile<P>::TR, TW = PcsTile<P>::TW;
   PCS_REQUIRE(B <= 65535 && (H + CCL_TR - 1) / CCL_TR <= 65535, "grid too large for the tile kernel");
-  dim3 gt((WW + 31) / 32, (H + CCL_TR - 1) / CCL_TR, B);
+  dim3 gt((WW + TW - 1) / TW, (H + CCL_TR - 1) / CCL_TR, B);
+  const int ntop = (H + CCL_TR - 1) / CCL_TR;
+  const int per_slice = ntop * WW + (H - ntop) * 2 * ((WW + TW - 1) / TW);  // tile-edge words of one slice
+  unsigned ge = pcs_blocks((long long)B * per_slice, PCS_CCL_THREADS);
   if (conn == 8) {
-    PCS_LAUNCH("k_ccl_tile", st, (k_ccl_tile<P, 8><<<gt, CCL_TR * 32, 0, st>>>(prov, ws.parent)));
-    PCS_LAUNCH("k_ccl_merge_edges", st, (k_ccl_merge_edges<P, 8><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, B)));
+    PCS_LAUNCH("k_ccl_tile", st, (k_ccl_tile<P, 8><<<gt, CCL_TILE_THREADS, 0, st>>>(prov, ws.parent)));
+    PCS_LAUNCH("k_ccl_merge_edges", st, (k_ccl_merge_edges<P, 8><<<ge, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, B, per_slice)));
   } else {
-    PCS_LAUNCH("k_ccl_tile", st, (k_ccl_tile<P, 4><<<gt, CCL_TR * 32, 0, st>>>(prov, ws.parent)));
-    PCS_LAUNCH("k_ccl_merge_edges", st, (k_ccl_merge_edges<P, 4><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, B)));
+    PCS_LAUNCH("k_ccl_tile", st, (k_ccl_tile<P, 4><<<gt, CCL_TILE_THREADS, 0, st>>>(prov, ws.parent)));
+    PCS_LAUNCH("k_ccl_merge_edges", st, (k_ccl_merge_edges<P, 4><<<ge, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, B, per_slice)));
   }
   PCS_LAUNCH("k_ccl_flatten", st, k_ccl_flatten<P><<<gc, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, ws.rootbits, ws.chunk, zero_aux ? ws.aux : nullptr, B, CPR));
   if (counts) {

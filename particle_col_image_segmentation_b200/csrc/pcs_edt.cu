@@ -165,7 +165,7 @@ __global__ void k_edt_lut_init() {
 __global__ void __launch_bounds__(EDT_TW)
     k_edt_near(const uint32_t* __restrict__ vw, const uint16_t* __restrict__ up, const uint16_t* __restrict__ dn,
                double* __restrict__ dist, int32_t* __restrict__ sq, uint32_t* __restrict__ thr_bits, int thr_sq,
-               uint8_t* __restrict__ row_far, int H, int W, int WW, int NB) {
+               uint8_t* __restrict__ row_far, int H, int W, int WW, int NB, int zero_fill) {
   __shared__ uint16_t g[32][EDT_TWH];
   __shared__ uint32_t tb[32][EDT_TW / 32];
   const int tid = threadIdx.x;
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(EDT_TW)
   for (int i = tid; i < 32 * EDT_TWH / 2; i += EDT_TW) gz[i] = 0u;
   // zero the outputs of the whole tile with 16-byte stores
   const long long obase = (b * H + (q << 5)) * (long long)W + x0;
-  if (dist) {
+  if (dist && zero_fill) {
     if (cols == EDT_TW && (W & 1) == 0) {
       for (int i = tid; i < rows * (EDT_TW / 2); i += EDT_TW) {
         const int r = i / (EDT_TW / 2), c = (i % (EDT_TW / 2)) * 2;
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(EDT_TW)
       }
     }
   }
-  if (sq) {
+  if (sq && zero_fill) {
     if (cols == EDT_TW && (W & 3) == 0) {
       for (int i = tid; i < rows * (EDT_TW / 4); i += EDT_TW) {
         const int r = i / (EDT_TW / 4), c = (i % (EDT_TW / 4)) * 4;
@@ -368,9 +368,17 @@ int pcs_edt_bits(const uint32_t* bits, int invert, int B, int H, int W, double* 
       lut_ready[dev] = true;
     }
   }
+  // background pixels are at distance 0: large outputs are cleared by the copy-engine-speed memset and the
+  // near kernel then only writes foreground pixels; small ones are zero-filled by the kernel itself
+  const size_t npx = (size_t)B * H * W;
+  const int zero_fill = npx < ((size_t)1 << 22);
+  if (!zero_fill) {
+    if (dist) cudaMemsetAsync(dist, 0, npx * sizeof(double), st);
+    if (sq) cudaMemsetAsync(sq, 0, npx * sizeof(int32_t), st);
+  }
   dim3 gn((W + EDT_TW - 1) / EDT_TW, NB, B);
   PCS_LAUNCH("k_edt_near", st,
-             k_edt_near<<<gn, EDT_TW, 0, st>>>(vw, up, dn, dist, sq, thr_bits, thr_sq, row_far, H, W, WW, NB));
+             k_edt_near<<<gn, EDT_TW, 0, st>>>(vw, up, dn, dist, sq, thr_bits, thr_sq, row_far, H, W, WW, NB, zero_fill));
   int W2 = 1, L = 0;
   while (W2 <= W) {
     W2 <<= 1;
