@@ -168,7 +168,10 @@ __global__ void __launch_bounds__(EDT_TW)
                uint8_t* __restrict__ row_far, int H, int W, int WW, int NB, int zero_fill) {
   __shared__ uint16_t g[32][EDT_TWH];
   __shared__ uint32_t tb[32][EDT_TW / 32];
+  __shared__ unsigned short items[32 * EDT_TW];  // (row << 9 | tile column) of the tile's foreground pixels
+  __shared__ int nitems;
   const int tid = threadIdx.x;
+  if (tid == 0) nitems = 0;
   const int Wp = WW << 5;
   const int x0 = blockIdx.x * EDT_TW;
   const int q = blockIdx.y;
@@ -208,22 +211,52 @@ __global__ void __launch_bounds__(EDT_TW)
     }
   }
   __syncthreads();
+  // pass 1: vertical distances of the foreground pixels; the tile's own foreground pixels are also
+  // appended to a work list so that pass 2 spreads them evenly over the CTA (a thread per pixel,
+  // not a thread per column: columns through a particle would serialise ~20 searches)
   for (int col = tid; col < EDT_TWH; col += EDT_TW) {
     const int x = x0 - EDT_HALO + col;
+    uint32_t f = 0;
     if (x >= 0 && x < W) {
-      uint32_t f = __ldg(vw + band + x);  // set bits = foreground rows of this column
+      f = __ldg(vw + band + x);  // set bits = foreground rows of this column
       if (f) {
         const uint32_t z = ~f;
         const uint32_t cu = __ldg(up + band + x), cd = __ldg(dn + band + x);
-        while (f) {
-          const int r = __ffs(f) - 1;
-          f &= f - 1;
+        uint32_t ff = f;
+        while (ff) {
+          const int r = __ffs(ff) - 1;
+          ff &= ff - 1;
           g[r][col] = (uint16_t)edt_vdist(z, r, cu, cd);
         }
       }
     } else {
 #pragma unroll 8
       for (int r = 0; r < 32; ++r) g[r][col] = (uint16_t)EDT_INF;  // outside the image: no site
+    }
+    // work items of interior columns (warp-level exclusive scan of the per-column counts)
+    const bool interior = col >= EDT_HALO && col < EDT_HALO + EDT_TW && x < W;
+    if (rows < 32) f &= (1u << rows) - 1u;
+    const int cnt = interior ? __popc(f) : 0;
+    const unsigned act = __activemask();
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int tv = __shfl_up_sync(act, incl, o);
+      if ((tid & 31) >= o) incl += tv;
+    }
+    const int last = 31 - __clz(act);
+    int wtot = __shfl_sync(act, incl, last);
+    int wbase = 0;
+    if ((tid & 31) == last && wtot) wbase = atomicAdd(&nitems, wtot);
+    wbase = __shfl_sync(act, wbase, last);
+    if (cnt) {
+      int pos = wbase + incl - cnt;
+      uint32_t ff = f;
+      while (ff) {
+        const int r = __ffs(ff) - 1;
+        ff &= ff - 1;
+        items[pos++] = (unsigned short)((r << 9) | col);
+      }
     }
   }
   __syncthreads();
@@ -237,30 +270,29 @@ __global__ void __launch_bounds__(EDT_TW)
     }
     __syncthreads();
   }
-  if (x < W) {
-    uint32_t f = __ldg(vw + band + x);
-    if (rows < 32) f &= (1u << rows) - 1u;
-    while (f) {
-      const int r = __ffs(f) - 1;
-      f &= f - 1;
-      const uint32_t gx = g[r][col];
-      const int y = (q << 5) + r;
-      if (gx > EDT_DMAX) {
-        row_far[b * H + y] = 1;  // solved by k_edt_far
-        continue;
-      }
-      uint32_t best = gx * gx;
-      for (uint32_t dd = 1; dd * dd < best; ++dd) {  // dd < gx <= EDT_HALO: stays inside the tile + halo
-        const uint32_t d2d = dd * dd;
-        const uint32_t g1 = g[r][col - (int)dd], g2 = g[r][col + (int)dd];
-        if (g1 != EDT_INF) best = min(best, d2d + g1 * g1);
-        if (g2 != EDT_INF) best = min(best, d2d + g2 * g2);
-      }
-      const long long o = (b * H + y) * (long long)W + x;
-      if (dist) dist[o] = g_edt_sqrt_lut[best];
-      if (sq) sq[o] = (int32_t)best;
-      if (thr_bits && (int)best <= thr_sq) atomicOr(&tb[r][tid >> 5], 1u << (tid & 31));
+  // pass 2: thread per foreground pixel
+  const int n = nitems;
+  for (int it = tid; it < n; it += EDT_TW) {
+    const int item = items[it];
+    const int r = item >> 9, c = item & 511;
+    const int px = x0 - EDT_HALO + c;
+    const uint32_t gx = g[r][c];
+    const int y = (q << 5) + r;
+    if (gx > EDT_DMAX) {
+      row_far[b * H + y] = 1;  // solved by k_edt_far
+      continue;
     }
+    uint32_t best = gx * gx;
+    for (uint32_t dd = 1; dd * dd < best; ++dd) {  // dd < gx <= EDT_HALO: stays inside the tile + halo
+      const uint32_t d2d = dd * dd;
+      const uint32_t g1 = g[r][c - (int)dd], g2 = g[r][c + (int)dd];
+      if (g1 != EDT_INF) best = min(best, d2d + g1 * g1);
+      if (g2 != EDT_INF) best = min(best, d2d + g2 * g2);
+    }
+    const long long o = (b * H + y) * (long long)W + px;
+    if (dist) dist[o] = g_edt_sqrt_lut[best];
+    if (sq) sq[o] = (int32_t)best;
+    if (thr_bits && (int)best <= thr_sq) atomicOr(&tb[r][(c - EDT_HALO) >> 5], 1u << ((c - EDT_HALO) & 31));
   }
   if (thr_bits) {
     __syncthreads();
