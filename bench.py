@@ -32,21 +32,23 @@ SUM_OF_STAGES_BYTES_PER_VOXEL = 27.0
 KERNEL_BYTES_PER_VOXEL = {
     "k_hist_u16": 2.0,
     "k_compare": 2.0 + 0.125,
-    "k_majority_bits": 0.25,
+    "k_majority5_bits": 0.25 + 1.0,
     "k_unpack": 1.0 + 0.125,
-    "k_ccl_init": 0.125,
-    "k_ccl_merge": 0.125,
+    "k_ccl_tile": 0.125,
+    "k_ccl_merge_edges": 0.125,
     "k_ccl_flatten": 0.125,
     "k_ccl_rank": 0.125,
     "k_ccl_relabel": 4.0 + 0.125,
     "k_ccl_mark": 0.125,
-    "k_ccl_select": 0.25,
+    "k_ccl_select": 0.25 + 1.0,
+    "k_bbox_raster": 0.125,
+    "k_hole_candidates": 0.5,
     "k_region_table": 4.0 + 2.0,
     "k_region_table_bits": 4.0 + 2.0,
     "k_select_by_area": 0.25,
     "k_edt_transpose": 0.25,
     "k_edt_carry": 0.25,
-    "k_edt_near": 8.0 + 0.25,
+    "k_edt_near": 8.0 + 0.25,  # the zero background is written by the memset that precedes it (same 8 B/voxel, counted here)
     "k_edt_far": 8.0 + 0.25,
 }
 
