@@ -67,6 +67,7 @@ def parse():
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--streams", type=int, default=1, help="streams the chunks of a step are spread over")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a captured CUDA graph")
     return ap.parse_args()
 
@@ -235,7 +236,7 @@ def run_b200(args):
     # graph (same kernels, same order) for the timed pass
     plan_eager = split_zstack.SegmentPlan(stack, chunk=args.chunk, z0=rank * Z)
     res = plan_eager.out
-    plan = split_zstack.SegmentPlan(stack, chunk=args.chunk, z0=rank * Z, out=None, graph=True) if not args.no_graph else plan_eager
+    plan = split_zstack.SegmentPlan(stack, chunk=args.chunk, z0=rank * Z, out=None, graph=True, streams=args.streams) if not args.no_graph else plan_eager
 
     def step(p=None):
         r = (p or plan)()
@@ -359,7 +360,7 @@ def run_b200(args):
         "vs_baseline": None,
         "dtype": "u16",
         "data": "synthetic",
-        "config": {"workload": f"split_zstack + segment a synthetic {S}x{S}x{Z} uint16 z-stack per GPU (BASELINE.json configs[1])", "size": S, "slices_per_gpu": Z, "chunk": args.chunk, "launch": "eager" if args.no_graph else "cuda graph replay (one graph per step)",
+        "config": {"workload": f"split_zstack + segment a synthetic {S}x{S}x{Z} uint16 z-stack per GPU (BASELINE.json configs[1])", "size": S, "slices_per_gpu": Z, "chunk": args.chunk, "streams": args.streams, "launch": "eager" if args.no_graph else "cuda graph replay (one graph per step)",
                    "l2": "input stack (%.0f MiB) and outputs are larger than L2; no flush needed" % (Z * S * S * 2 / 2**20), "parity_spot_check": parity},
         "clocks": clocks,
         "e2e": e2e,

@@ -102,7 +102,7 @@ class SegmentPlan:
     latency matters).  ``plan()`` is asynchronous and returns the bound ``SegmentResult``.
     """
 
-    def __init__(self, stack, denoise_size=5, min_size=20, chunk=16, max_regions_per_slice=1 << 14, out=None, z0=0, graph=False):
+    def __init__(self, stack, denoise_size=5, min_size=20, chunk=16, max_regions_per_slice=1 << 14, out=None, z0=0, graph=False, streams=1):
         ops.require_cuda(stack, "stack")
         if stack.dtype != torch.uint16 or stack.dim() != 3:
             raise _lib.PcsError(f"segment pipeline expects a (Z, H, W) uint16 tensor, got {tuple(stack.shape)} {stack.dtype}")
@@ -126,8 +126,13 @@ class SegmentPlan:
         out.tables = []
         self.calls = []
         nws = self.lib.pcs_segment_workspace_bytes(chunk, H, W)
-        self.ws = torch.empty(nws, dtype=torch.uint8, device=dev)  # owned: graph replays need stable pointers
-        for a in range(0, Z, chunk):
+        n_chunks = (Z + chunk - 1) // chunk
+        # chunks are independent (slices are): with several streams their kernels overlap, which fills
+        # the SMs while the latency-bound union-find / search kernels of another chunk are in flight
+        self.n_streams = max(1, min(int(streams), n_chunks))
+        self.side = [torch.cuda.Stream(device=dev) for _ in range(self.n_streams - 1)]
+        self.ws = [torch.empty(nws, dtype=torch.uint8, device=dev) for _ in range(self.n_streams)]  # owned: stable pointers for graph replays
+        for i, a in enumerate(range(0, Z, chunk)):
             b = min(Z, a + chunk)
             B = b - a
             offsets = torch.empty(B + 1, dtype=torch.int32, device=dev)
@@ -135,8 +140,9 @@ class SegmentPlan:
             table = torch.empty((ops.TABLE_COLS, cap), dtype=torch.int64, device=dev)
             out.tables.append((a, offsets, table))
             P = ops._p
+            ws = self.ws[i % self.n_streams]
             self.calls.append((P(stack[a:b]), B, H, W, self.dn, self.ms, P(out.mask[a:b]), P(out.labels[a:b]), P(out.refined[a:b]), P(out.edt[a:b]),
-                               P(out.threshold[a:b]), P(out.counts[a:b]), P(offsets), P(table), cap, P(self.ws), nws))
+                               P(out.threshold[a:b]), P(out.counts[a:b]), P(offsets), P(table), cap, P(ws), nws))
         self.graph = None
         if graph:
             self._enqueue()  # warm-up: one-time initialisations must not land in the capture
@@ -147,9 +153,18 @@ class SegmentPlan:
             self.graph = g
 
     def _enqueue(self):
-        st = ops._stream()
-        for c in self.calls:
-            _lib.check(self.lib.pcs_segment_chunk(*c, st), "pcs_segment_chunk")
+        main = torch.cuda.current_stream()
+        for s in self.side:
+            s.wait_stream(main)  # fork
+        for i, c in enumerate(self.calls):
+            j = i % self.n_streams
+            if j == 0:
+                _lib.check(self.lib.pcs_segment_chunk(*c, main.cuda_stream), "pcs_segment_chunk")
+            else:
+                with torch.cuda.stream(self.side[j - 1]):
+                    _lib.check(self.lib.pcs_segment_chunk(*c, self.side[j - 1].cuda_stream), "pcs_segment_chunk")
+        for s in self.side:
+            main.wait_stream(s)  # join
 
     def __call__(self):
         if self.graph is not None:
