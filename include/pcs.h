@@ -108,6 +108,14 @@ size_t pcs_fill_holes_table_workspace_bytes(int B, int H, int W);
 int pcs_fill_holes_table_bits(const uint32_t* bits, const int64_t* table, int64_t cap, const int32_t* offsets, int64_t min_size,
                               uint32_t* out, uint8_t* out_mask /* optional uint8 copy */, int B, int H, int W, void* ws, size_t ws_bytes,
                               void* stream);
+/* remove_small_objects(min_size, 8-connected) followed by binary_fill_holes when the 8-connected components
+ * of `bits` are already labelled (`labels` int32, any numbering) and their areas sit in column 0 of `table`
+ * (tiff_analysis.py:769-773 then :880).  Only row gaps bounded by two runs of one label can hold hole pixels,
+ * so just those are labelled.  table / offsets may be null when min_size <= 1.  Workspace:
+ * pcs_fill_holes_table_workspace_bytes. */
+int pcs_refine_labeled_bits(const uint32_t* bits, const int32_t* labels, const int64_t* table, int64_t cap, const int32_t* offsets,
+                            int64_t min_size, uint32_t* out, uint8_t* out_mask /* optional uint8 copy */, int B, int H, int W, void* ws,
+                            size_t ws_bytes, void* stream);
 /* skimage.morphology.remove_small_objects (area filter of tiff_analysis.py:769-773); ws needs with_aux = 1 */
 int pcs_remove_small_bits(const uint32_t* bits, uint32_t* out, int B, int H, int W, int connectivity, int min_size, void* ws, size_t ws_bytes, void* stream);
 /* components of `bits` that contain a seed pixel (merged_image, tiff_analysis.py:843-878) */

@@ -55,6 +55,7 @@ SIGNATURES = {
     "pcs_fill_holes_bits": (c_int, [_P, _P, _I, _I, _I, _P, _Z, _P]),
     "pcs_fill_holes_table_workspace_bytes": (_Z, [_I, _I, _I]),
     "pcs_fill_holes_table_bits": (c_int, [_P, _P, _L, _P, _L, _P, _P, _I, _I, _I, _P, _Z, _P]),
+    "pcs_refine_labeled_bits": (c_int, [_P, _P, _P, _L, _P, _L, _P, _P, _I, _I, _I, _P, _Z, _P]),
     "pcs_remove_small_bits": (c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _Z, _P]),
     "pcs_select_components_bits": (c_int, [_P, _P, _P, _I, _I, _I, _I, _P, _Z, _P]),
     "pcs_local_maxima_conn": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _Z, _P]),

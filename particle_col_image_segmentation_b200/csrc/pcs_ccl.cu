@@ -757,6 +757,168 @@ __global__ void __launch_bounds__(256)
   seed[t] = M;
 }
 
+
+// ---------------------------------------------------------------- refine: small objects out + hole candidates by row spans
+// Hole filling when the foreground is already labelled (the pipeline's case).  The outer boundary
+// of a hole is an 8-connected curve of ONE component, so every hole pixel has pixels of that
+// component both to its left and to its right in its own row (possibly beyond islands that sit in
+// the hole).  Background outside every same-label row span can therefore never be part of a hole.
+// The candidate set C = background between two runs of one label in a row is tiny for blob-like
+// masks (convex blobs have none).  Holes = 4-connected components of C that neither touch the image
+// border nor touch background outside C.  Any superset of C gives the same answer, which the
+// bounded search below relies on.
+//
+// k_refine_rows: warp per row.  Drops the runs of components below min_size (area from the region
+// table: remove_small_objects), lists the kept runs of the row in shared memory, pairs every run
+// with the previous run of the same label (looking back at most REFINE_K runs; if the window is
+// exhausted the whole row prefix becomes candidate, a safe superset) and paints the spans: partial
+// words with shared atomics, whole words through a difference array + prefix sum.
+#define REFINE_MAX_WARPS 8
+#define REFINE_K 48
+#define REFINE_RMAX 256  // kept runs listed per row; a row with more becomes candidate as a whole (safe superset)
+#define REFINE_SMEM_LIMIT (200 * 1024)
+static inline size_t refine_words_per_warp(int WW) { return (size_t)WW * 3 + 1 + 2 * REFINE_RMAX; }
+
+__device__ __forceinline__ void refine_paint(uint32_t* cb, int* diff, int a, int e) {
+  const int wa = a >> 5, we = e >> 5;
+  const uint32_t ma = 0xffffffffu << (a & 31), me = 0xffffffffu >> (31 - (e & 31));
+  if (wa == we) {
+    atomicOr(cb + wa, ma & me);
+  } else {
+    atomicOr(cb + wa, ma);
+    atomicOr(cb + we, me);
+    if (we - wa > 1) {
+      atomicAdd(diff + wa + 1, 1);
+      atomicAdd(diff + we, -1);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(REFINE_MAX_WARPS * 32)
+    k_refine_rows(const uint32_t* __restrict__ fg, const int32_t* __restrict__ labels, const long long* __restrict__ table,
+                  long long cap, const int* __restrict__ offsets, long long min_size, uint32_t* __restrict__ kept_out,
+                  uint32_t* __restrict__ cand_out, long long rows, int H, int W, int WW) {
+  extern __shared__ uint32_t sm[];
+  const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + wl;
+  if (row >= rows) return;
+  uint32_t* kw = sm + (size_t)wl * ((size_t)WW * 3 + 1 + 2 * REFINE_RMAX);  // kept words of the row
+  uint32_t* cb = kw + WW;                                                     // painted partial words
+  int* diff = (int*)(cb + WW);                                                // WW + 1: whole-word coverage, differenced
+  int* rl = diff + WW + 1;                                                    // labels of the kept runs, row order
+  uint32_t* rse = (uint32_t*)(rl + REFINE_RMAX);                              // start | end << 16 of the kept runs
+  for (int k = lane; k < WW; k += 32) {
+    cb[k] = 0u;
+    diff[k] = 0;
+  }
+  if (lane == 0) diff[WW] = 0;
+  const long long b = row / H;
+  const long long tbase = offsets ? (long long)offsets[b] : 0;
+  const int32_t* lrow = labels + row * (long long)W;
+  const uint32_t* frow = fg + row * (long long)WW;
+  int n = 0;
+  bool overflow = false;
+  for (int k0 = 0; k0 < WW; k0 += 32) {
+    const int k = k0 + lane;
+    const uint32_t f = k < WW ? __ldg(frow + k) : 0u;
+    uint32_t kept = f;
+    int cnt = __popc(f & ~(f << 1));
+    if (min_size > 1) {
+      kept = 0u;
+      cnt = 0;
+      uint32_t S = f & ~(f << 1);
+      while (S) {
+        const int s = __ffs(S) - 1;
+        S &= S - 1;
+        const uint32_t upper = ~(f >> s);
+        const int len = upper ? (__ffs(upper) - 1) : 32;
+        const long long r = tbase + __ldg(lrow + (k << 5) + s) - 1;
+        if (r < 0 || r >= cap || __ldg(table + r) < min_size) continue;  // column 0 of the table: area
+        kept |= (len >= 32 ? 0xffffffffu : ((1u << len) - 1u)) << s;
+        ++cnt;
+      }
+    }
+    int tot;
+    int at = n + pcs_warp_excl_scan(cnt, lane, &tot);
+    n += tot;
+    overflow |= n > REFINE_RMAX;
+    if (!overflow) {
+      uint32_t S = kept & ~(kept << 1);
+      while (S) {  // labels come back from L1 this time
+        const int s = __ffs(S) - 1;
+        S &= S - 1;
+        const uint32_t upper = ~(kept >> s);
+        const int len = upper ? (__ffs(upper) - 1) : 32;
+        const uint32_t xs = (uint32_t)((k << 5) + s);
+        rl[at] = __ldg(lrow + xs);
+        rse[at] = xs | ((xs + len - 1) << 16);
+        ++at;
+      }
+    }
+    if (k < WW) {
+      kw[k] = kept;
+      kept_out[row * (long long)WW + k] = kept;
+    }
+  }
+  __syncwarp();
+  if (overflow) {
+    for (int k = lane; k < WW; k += 32) cand_out[row * (long long)WW + k] = ~kw[k] & pcs_valid_mask(k, W);
+    return;
+  }
+  int fb = -1;  // end of the row prefix painted when a search window ran out
+  for (int i = lane; i < n; i += 32) {
+    const int L = rl[i];
+    const int lo = max(i - REFINE_K, 0);
+    int j = i - 1;
+    while (j >= lo && rl[j] != L) --j;
+    const int e = (int)(rse[i] & 0xffffu) - 1;
+    if (j >= lo) {
+      const int a = (int)(rse[j] >> 16) + 1;
+      if (a <= e) refine_paint(cb, diff, a, e);
+    } else if (lo > 0) {
+      fb = max(fb, e);
+    }
+  }
+  fb = __reduce_max_sync(0xffffffffu, fb);
+  if (lane == 0 && fb >= 0) refine_paint(cb, diff, 0, fb);
+  __syncwarp();
+  int carry = 0;
+  for (int k0 = 0; k0 < WW; k0 += 32) {
+    const int k = k0 + lane;
+    const int d = k < WW ? diff[k] : 0;
+    int tot;
+    const int cov = carry + pcs_warp_excl_scan(d, lane, &tot) + d;
+    carry += tot;
+    if (k < WW) cand_out[row * (long long)WW + k] = (cb[k] | (cov > 0 ? 0xffffffffu : 0u)) & ~kw[k] & pcs_valid_mask(k, W);
+  }
+}
+
+// thread per word: seeds = candidate pixels on the top / bottom image row or 4-adjacent to background
+// that is not a candidate (such background is never part of a hole)
+__global__ void __launch_bounds__(256)
+    k_hole_seeds(const uint32_t* __restrict__ kept, const uint32_t* __restrict__ cand, uint32_t* __restrict__ seed, int B, int H,
+                 int W, int WW) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)B * H * WW;
+  if (t >= total) return;
+  const uint32_t C = cand[t];
+  uint32_t M = 0;
+  if (C) {
+    const int k = (int)(t % WW);
+    const int y = (int)((t / WW) % H);
+    auto open_at = [&](long long idx, int kk) { return ~kept[idx] & ~cand[idx] & pcs_valid_mask(kk, W); };
+    const uint32_t n_c = open_at(t, k);
+    uint32_t adj = (n_c << 1) | (n_c >> 1);
+    adj |= (k > 0) ? (open_at(t - 1, k - 1) >> 31) : 1u;
+    if (k + 1 < WW) adj |= open_at(t + 1, k + 1) << 31;
+    adj |= (y > 0) ? open_at(t - WW, k) : 0xffffffffu;
+    adj |= (y + 1 < H) ? open_at(t + WW, k) : 0xffffffffu;
+    adj |= 1u << ((W - 1) & 31) & ((k == WW - 1) ? 0xffffffffu : 0u);  // right image border
+    M = C & adj;
+  }
+  seed[t] = M;
+}
+
 // ============================================================== host drivers
 template <class P>
 static int ccl_forest(const P& prov, int B, int conn, const PcsCclWs& ws, int32_t* counts, int zero_aux, cudaStream_t st) {
@@ -885,6 +1047,49 @@ int pcs_fill_holes_table_bits(const uint32_t* bits, const int64_t* table, int64_
   PCS_LAUNCH("k_ccl_mark", st, (k_ccl_mark<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, seed, 1, B)));
   PCS_LAUNCH("k_ccl_select", st, (k_ccl_select<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, 0, bits, nullptr, out, out_mask, B)));
   return pcs_check_launch("fill holes (table)");
+}
+
+int pcs_refine_labeled_bits(const uint32_t* bits, const int32_t* labels, const int64_t* table, int64_t cap, const int32_t* offsets,
+                            int64_t min_size, uint32_t* out, uint8_t* out_mask, int B, int H, int W, void* wsp, size_t ws_bytes,
+                            void* stream) {
+  int rc = check_dims(B, H, W);
+  if (rc) return rc;
+  PCS_REQUIRE(bits && labels && out, "null argument");
+  PCS_REQUIRE(min_size <= 1 || (table && offsets && cap >= 1), "min_size > 1 needs the region table");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int WW = pcs_words(W);
+  const size_t plane = pcs_align256((size_t)B * H * WW * 4);
+  if (wsp == nullptr || ws_bytes < pcs_ccl_ws_bytes(B, H, W, 0) + 3 * plane) {
+    pcs_set_error("refine workspace too small (see pcs_fill_holes_table_workspace_bytes)");
+    return PCS_ERR_WORKSPACE;
+  }
+  PcsCclWs ws;
+  rc = pcs_ccl_ws_carve(wsp, ws_bytes, B, H, W, 0, &ws);
+  if (rc) return rc;
+  char* extra = (char*)wsp + pcs_ccl_ws_bytes(B, H, W, 0);
+  uint32_t* kept = (uint32_t*)extra;
+  uint32_t* cand = (uint32_t*)(extra + plane);
+  uint32_t* seed = (uint32_t*)(extra + 2 * plane);
+  const long long rows = (long long)B * H;
+  const size_t warp_bytes = refine_words_per_warp(WW) * 4;
+  int warps = (int)(REFINE_SMEM_LIMIT / warp_bytes);
+  PCS_REQUIRE(warps >= 1, "row too wide for the refine kernel");
+  if (warps > REFINE_MAX_WARPS) warps = REFINE_MAX_WARPS;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_refine_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, REFINE_SMEM_LIMIT);
+    attr_set = true;
+  }
+  PCS_LAUNCH("k_refine_rows", st, (k_refine_rows<<<pcs_blocks(rows, warps), warps * 32, warps * warp_bytes, st>>>(
+      bits, labels, (const long long*)table, cap, offsets, min_size, kept, cand, rows, H, W, WW)));
+  unsigned gw = pcs_blocks((long long)B * H * WW, PCS_CCL_THREADS);
+  PCS_LAUNCH("k_hole_seeds", st, (k_hole_seeds<<<gw, 256, 0, st>>>(kept, cand, seed, B, H, W, WW)));
+  PcsBinProv prov{cand, H, W, WW, 0};
+  rc = ccl_forest(prov, B, 4, ws, nullptr, 0, st);
+  if (rc) return rc;
+  PCS_LAUNCH("k_ccl_mark", st, (k_ccl_mark<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, seed, 1, B)));
+  PCS_LAUNCH("k_ccl_select", st, (k_ccl_select<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, 0, kept, nullptr, out, out_mask, B)));
+  return pcs_check_launch("refine (labelled)");
 }
 
 size_t pcs_fill_holes_table_workspace_bytes(int B, int H, int W) {

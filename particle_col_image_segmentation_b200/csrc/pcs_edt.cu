@@ -54,12 +54,14 @@ __global__ void __launch_bounds__(256)
     w = bits[(b * H + y) * (long long)WW + k];
     if (invert) w = ~w;
   }
-  uint32_t mine = 0;
+  // 32x32 bit transpose across the warp: five block-swap steps (lane = row in, lane = column out)
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    uint32_t v = __ballot_sync(0xffffffffu, (w >> i) & 1u);
-    if (lane == i) mine = v;
+  for (int j = 16; j >= 1; j >>= 1) {
+    const uint32_t m = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu : j == 2 ? 0x33333333u : 0x55555555u;
+    const uint32_t other = __shfl_xor_sync(0xffffffffu, w, j);
+    w = (lane & j) ? ((w & ~m) | ((other & ~m) >> j)) : ((w & m) | ((other & m) << j));
   }
+  const uint32_t mine = w;
   vw[(b * NB + q) * (long long)(WW << 5) + (k << 5) + lane] = mine;
 }
 
@@ -157,16 +159,19 @@ __global__ void k_edt_lut_init() {
 
 // Phase 1: CTA per (column tile, band, slice).  Every pixel whose vertical distance is at most
 // EDT_DMAX is final after an outward search inside the tile + halo; the others flag their row.
-// Background pixels (the vast majority) are written by vectorised zero stores; only foreground
-// pixels are visited individually, column by column off the vertical bit words.
+// Only foreground pixels are visited individually (a balanced work list built off the vertical bit
+// words); their squared distances land in a shared tile that starts at zero, and the whole tile is
+// then written once with 16-byte coalesced stores -- 8 B/pixel of output traffic, no separate clear.
 #define EDT_TW 256
 #define EDT_HALO 40
 #define EDT_TWH (EDT_TW + 2 * EDT_HALO)
+#define EDT_GCLAMP 255u  // vertical distances above EDT_DMAX never win a near search: 8 bits are enough
 __global__ void __launch_bounds__(EDT_TW)
     k_edt_near(const uint32_t* __restrict__ vw, const uint16_t* __restrict__ up, const uint16_t* __restrict__ dn,
                double* __restrict__ dist, int32_t* __restrict__ sq, uint32_t* __restrict__ thr_bits, int thr_sq,
-               uint8_t* __restrict__ row_far, int H, int W, int WW, int NB, int zero_fill) {
-  __shared__ uint16_t g[32][EDT_TWH];
+               uint8_t* __restrict__ row_far, int H, int W, int WW, int NB) {
+  __shared__ __align__(16) uint8_t g[32][EDT_TWH];
+  __shared__ __align__(16) uint16_t d2s[32][EDT_TW];
   __shared__ uint32_t tb[32][EDT_TW / 32];
   __shared__ unsigned short items[32 * EDT_TW];  // (row << 9 | tile column) of the tile's foreground pixels
   __shared__ int nitems;
@@ -179,36 +184,12 @@ __global__ void __launch_bounds__(EDT_TW)
   const long long band = (b * NB + q) * (long long)Wp;
   const int rows = min(32, H - (q << 5));
   const int cols = min(EDT_TW, W - x0);
-  // background pixels have g = 0: clear the tile, then visit only the foreground rows of each column
-  uint32_t* gz = reinterpret_cast<uint32_t*>(&g[0][0]);
-  for (int i = tid; i < 32 * EDT_TWH / 2; i += EDT_TW) gz[i] = 0u;
-  // zero the outputs of the whole tile with 16-byte stores
-  const long long obase = (b * H + (q << 5)) * (long long)W + x0;
-  if (dist && zero_fill) {
-    if (cols == EDT_TW && (W & 1) == 0) {
-      for (int i = tid; i < rows * (EDT_TW / 2); i += EDT_TW) {
-        const int r = i / (EDT_TW / 2), c = (i % (EDT_TW / 2)) * 2;
-        *reinterpret_cast<double2*>(dist + obase + (long long)r * W + c) = make_double2(0.0, 0.0);
-      }
-    } else {
-      for (int i = tid; i < rows * EDT_TW; i += EDT_TW) {
-        const int r = i / EDT_TW, c = i % EDT_TW;
-        if (c < cols) dist[obase + (long long)r * W + c] = 0.0;
-      }
-    }
-  }
-  if (sq && zero_fill) {
-    if (cols == EDT_TW && (W & 3) == 0) {
-      for (int i = tid; i < rows * (EDT_TW / 4); i += EDT_TW) {
-        const int r = i / (EDT_TW / 4), c = (i % (EDT_TW / 4)) * 4;
-        *reinterpret_cast<int4*>(sq + obase + (long long)r * W + c) = make_int4(0, 0, 0, 0);
-      }
-    } else {
-      for (int i = tid; i < rows * EDT_TW; i += EDT_TW) {
-        const int r = i / EDT_TW, c = i % EDT_TW;
-        if (c < cols) sq[obase + (long long)r * W + c] = 0;
-      }
-    }
+  // background pixels have g = 0 and distance 0: clear both tiles, then visit only the foreground
+  {
+    uint4* gz = reinterpret_cast<uint4*>(&g[0][0]);
+    for (int i = tid; i < 32 * EDT_TWH / 16; i += EDT_TW) gz[i] = make_uint4(0, 0, 0, 0);
+    uint4* dz = reinterpret_cast<uint4*>(&d2s[0][0]);
+    for (int i = tid; i < 32 * EDT_TW / 8; i += EDT_TW) dz[i] = make_uint4(0, 0, 0, 0);
   }
   __syncthreads();
   // pass 1: vertical distances of the foreground pixels; the tile's own foreground pixels are also
@@ -226,12 +207,12 @@ __global__ void __launch_bounds__(EDT_TW)
         while (ff) {
           const int r = __ffs(ff) - 1;
           ff &= ff - 1;
-          g[r][col] = (uint16_t)edt_vdist(z, r, cu, cd);
+          g[r][col] = (uint8_t)min(edt_vdist(z, r, cu, cd), EDT_GCLAMP);
         }
       }
     } else {
 #pragma unroll 8
-      for (int r = 0; r < 32; ++r) g[r][col] = (uint16_t)EDT_INF;  // outside the image: no site
+      for (int r = 0; r < 32; ++r) g[r][col] = (uint8_t)EDT_GCLAMP;  // outside the image: no site
     }
     // work items of interior columns (warp-level exclusive scan of the per-column counts)
     const bool interior = col >= EDT_HALO && col < EDT_HALO + EDT_TW && x < W;
@@ -260,12 +241,11 @@ __global__ void __launch_bounds__(EDT_TW)
     }
   }
   __syncthreads();
-  const int x = x0 + tid;
-  const int col = tid + EDT_HALO;
   if (thr_bits) {
     // background pixels are at distance 0: start every row word from them (warp w owns word w)
+    const int x = x0 + tid;
     for (int r = 0; r < 32; ++r) {
-      unsigned bg = __ballot_sync(0xffffffffu, x < W && g[r][col] == 0u);
+      unsigned bg = __ballot_sync(0xffffffffu, x < W && g[r][tid + EDT_HALO] == 0u);
       if ((tid & 31) == 0) tb[r][tid >> 5] = thr_sq >= 0 ? bg : 0u;
     }
     __syncthreads();
@@ -275,27 +255,58 @@ __global__ void __launch_bounds__(EDT_TW)
   for (int it = tid; it < n; it += EDT_TW) {
     const int item = items[it];
     const int r = item >> 9, c = item & 511;
-    const int px = x0 - EDT_HALO + c;
     const uint32_t gx = g[r][c];
-    const int y = (q << 5) + r;
     if (gx > EDT_DMAX) {
-      row_far[b * H + y] = 1;  // solved by k_edt_far
+      row_far[b * H + (q << 5) + r] = 1;  // solved by k_edt_far, which rewrites the whole row
       continue;
     }
     uint32_t best = gx * gx;
     for (uint32_t dd = 1; dd * dd < best; ++dd) {  // dd < gx <= EDT_HALO: stays inside the tile + halo
       const uint32_t d2d = dd * dd;
       const uint32_t g1 = g[r][c - (int)dd], g2 = g[r][c + (int)dd];
-      if (g1 != EDT_INF) best = min(best, d2d + g1 * g1);
-      if (g2 != EDT_INF) best = min(best, d2d + g2 * g2);
+      best = min(best, min(d2d + g1 * g1, d2d + g2 * g2));  // clamped columns (255^2) never win
     }
-    const long long o = (b * H + y) * (long long)W + px;
-    if (dist) dist[o] = g_edt_sqrt_lut[best];
-    if (sq) sq[o] = (int32_t)best;
+    d2s[r][c - EDT_HALO] = (uint16_t)best;
     if (thr_bits && (int)best <= thr_sq) atomicOr(&tb[r][(c - EDT_HALO) >> 5], 1u << ((c - EDT_HALO) & 31));
   }
+  __syncthreads();
+  // write the tile: background zeros and foreground distances in one coalesced sweep
+  const long long obase = (b * H + (q << 5)) * (long long)W + x0;
+  if (dist) {
+    if (cols == EDT_TW && (W & 1) == 0 && ((((uintptr_t)dist) & 15) == 0)) {
+      for (int i = tid; i < rows * (EDT_TW / 2); i += EDT_TW) {
+        const int r = i / (EDT_TW / 2), c = (i % (EDT_TW / 2)) * 2;
+        const uint32_t pr = *reinterpret_cast<const uint32_t*>(&d2s[r][c]);
+        double2 v = make_double2(0.0, 0.0);
+        if (pr) {
+          v.x = g_edt_sqrt_lut[pr & 0xffffu];
+          v.y = g_edt_sqrt_lut[pr >> 16];
+        }
+        __stcs(reinterpret_cast<double2*>(dist + obase + (long long)r * W + c), v);
+      }
+    } else {
+      for (int i = tid; i < rows * EDT_TW; i += EDT_TW) {
+        const int r = i / EDT_TW, c = i % EDT_TW;
+        if (c < cols) dist[obase + (long long)r * W + c] = g_edt_sqrt_lut[d2s[r][c]];
+      }
+    }
+  }
+  if (sq) {
+    if (cols == EDT_TW && (W & 3) == 0 && ((((uintptr_t)sq) & 15) == 0)) {
+      for (int i = tid; i < rows * (EDT_TW / 4); i += EDT_TW) {
+        const int r = i / (EDT_TW / 4), c = (i % (EDT_TW / 4)) * 4;
+        const uint2 pr = *reinterpret_cast<const uint2*>(&d2s[r][c]);
+        *reinterpret_cast<int4*>(sq + obase + (long long)r * W + c) =
+            make_int4((int)(pr.x & 0xffffu), (int)(pr.x >> 16), (int)(pr.y & 0xffffu), (int)(pr.y >> 16));
+      }
+    } else {
+      for (int i = tid; i < rows * EDT_TW; i += EDT_TW) {
+        const int r = i / EDT_TW, c = i % EDT_TW;
+        if (c < cols) sq[obase + (long long)r * W + c] = (int32_t)d2s[r][c];
+      }
+    }
+  }
   if (thr_bits) {
-    __syncthreads();
     for (int i = tid; i < rows * (EDT_TW / 32); i += EDT_TW) {
       const int r = i / (EDT_TW / 32), w = i % (EDT_TW / 32);
       const int kw = (x0 >> 5) + w;
@@ -400,17 +411,9 @@ int pcs_edt_bits(const uint32_t* bits, int invert, int B, int H, int W, double* 
       lut_ready[dev] = true;
     }
   }
-  // background pixels are at distance 0: large outputs are cleared by the copy-engine-speed memset and the
-  // near kernel then only writes foreground pixels; small ones are zero-filled by the kernel itself
-  const size_t npx = (size_t)B * H * W;
-  const int zero_fill = npx < ((size_t)1 << 22);
-  if (!zero_fill) {
-    if (dist) cudaMemsetAsync(dist, 0, npx * sizeof(double), st);
-    if (sq) cudaMemsetAsync(sq, 0, npx * sizeof(int32_t), st);
-  }
   dim3 gn((W + EDT_TW - 1) / EDT_TW, NB, B);
   PCS_LAUNCH("k_edt_near", st,
-             k_edt_near<<<gn, EDT_TW, 0, st>>>(vw, up, dn, dist, sq, thr_bits, thr_sq, row_far, H, W, WW, NB, zero_fill));
+             k_edt_near<<<gn, EDT_TW, 0, st>>>(vw, up, dn, dist, sq, thr_bits, thr_sq, row_far, H, W, WW, NB));
   int W2 = 1, L = 0;
   while (W2 <= W) {
     W2 <<= 1;

@@ -73,13 +73,9 @@ int pcs_segment_chunk(const uint16_t* img, int B, int H, int W, int denoise_size
   STEP(pcs_label_bits(bits, B, H, W, 8, 0, labels, 4, counts, offsets, nullptr, 0, w.ccl, w.ccl_bytes, stream));
   STEP(pcs_table_init(table, cap, stream));
   STEP(pcs_region_table(labels, 4, img, 1, bits, nullptr, offsets, table, cap, B, H, W, stream));
-  const uint32_t* kept = bits;
-  if (min_size > 1) {
-    STEP(pcs_select_by_area(labels, bits, table, cap, offsets, min_size, w.keep, B, H, W, stream));
-    kept = w.keep;
-  }
-  // holes of the kept components lie inside their bounding boxes (from the table just built)
-  STEP(pcs_fill_holes_table_bits(kept, table, cap, offsets, min_size > 1 ? min_size : 1, w.refined, refined, B, H, W, w.ccl, w.ccl_bytes, stream));
+  // small objects out and holes filled in one call: areas come from the table just built, and only
+  // row gaps between two runs of one label can hold hole pixels
+  STEP(pcs_refine_labeled_bits(bits, labels, table, cap, offsets, min_size > 1 ? min_size : 1, w.refined, refined, B, H, W, w.ccl, w.ccl_bytes, stream));
   STEP(pcs_edt_bits(w.refined, 0, B, H, W, edt, nullptr, nullptr, 0, w.edt, w.edt_bytes, stream));
 #undef STEP
   return PCS_OK;

@@ -339,6 +339,20 @@ def region_table(labels, offsets, table, intensity=None, fg_bits=None, ov_bits=N
     return table
 
 
+def refine_labeled(bits, labels, table, offsets, min_size, W, want_mask=False):
+    """``remove_small_objects(min_size, 8-connected)`` then ``binary_fill_holes`` of a bit image whose
+    components are already labelled (``pcs_refine_labeled_bits``).  Returns bits (and the uint8 mask)."""
+    B, H, _ = bits.shape
+    lib = _lib.load()
+    n = lib.pcs_fill_holes_table_workspace_bytes(B, H, W)
+    ws = torch.empty(n, dtype=torch.uint8, device=bits.device)
+    out = torch.empty_like(bits)
+    mask = torch.empty((B, H, W), dtype=torch.uint8, device=bits.device) if want_mask else None
+    _lib.call("pcs_refine_labeled_bits", _p(bits), _p(labels), _p(table), int(table.shape[1]) if table is not None else 0, _p(offsets), int(min_size),
+              _p(out), _p(mask), B, H, W, _p(ws), n, _stream())
+    return (out, mask) if want_mask else out
+
+
 def select_labels(labels, keep):
     """Bit image of pixels whose label is flagged in ``keep`` (uint8 ``(B, n)``)."""
     B, H, W = _bhw(labels)

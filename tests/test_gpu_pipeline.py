@@ -128,3 +128,74 @@ def test_fill_holes_from_table_matches_scipy(seg):
         for i in range(B):
             assert np.array_equal(got[i], ndi.binary_fill_holes(m[i])), (shape, i)
         assert np.array_equal(mask.cpu().numpy().astype(bool), got)
+
+
+def _spiral(n):
+    """Square spiral wall, one pixel wide, lanes one pixel wide: concave everywhere, no hole."""
+    m = np.zeros((n, n), bool)
+    y = x = 0
+    dy, dx = 0, 1
+    seg = n - 1
+    m[0, 0] = True
+    turns = 0
+    while seg > 0:
+        for _ in range(seg):
+            y += dy
+            x += dx
+            m[y, x] = True
+        dy, dx = dx, -dy
+        turns += 1
+        if turns >= 3 and turns % 2 == 1:
+            seg -= 2
+    return m
+
+
+@pytest.mark.parametrize("min_size", [1, 6, 40])
+def test_refine_labeled_matches_scipy(seg, min_size):
+    """Row-gap candidates + seeds == remove_small_objects then scipy.ndimage.binary_fill_holes,
+    on shapes chosen to stress the candidate argument (spirals, C shapes, nested rings, islands in
+    holes, holes on the first / last rows and columns, wide gaps across many words)."""
+    from scipy import ndimage as ndi
+
+    from oracle.skimage_shim.morphology import remove_small_objects
+    from particle_col_image_segmentation_b200 import ops
+
+    rng = np.random.default_rng(17 + min_size)
+    cases = []
+    for shape, p in (((3, 70, 97), 0.55), ((2, 130, 257), 0.45), ((1, 64, 64), 0.8), ((2, 33, 65), 0.2), ((2, 50, 1100), 0.5), ((1, 200, 40), 0.6)):
+        cases.append(rng.random(shape) < p)
+    hand = np.zeros((4, 96, 200), bool)
+    hand[0, :41, :41] = _spiral(41)
+    hand[0, 50:90, 10:190] = True  # ring 150 px wide: the gap spans several words
+    hand[0, 55:85, 15:185] = False
+    hand[0, 60:80, 60:140] = True  # nested ring inside the hole
+    hand[0, 64:76, 64:136] = False
+    hand[0, 68:72, 90:100] = True  # island in the inner hole
+    hand[0, 69, 92] = False        # one-pixel hole in the island
+    hand[1, 0:20, 5:30] = True     # C open to the top border row
+    hand[1, 0:15, 10:25] = False
+    hand[1, 76:96, 5:30] = True    # closed by the bottom row? no: open to the bottom border
+    hand[1, 81:96, 10:25] = False
+    hand[1, 30:60, 0:25] = True    # ring touching the left border: still a hole
+    hand[1, 35:55, 1:20] = False
+    hand[1, 30:60, 170:200] = True  # C open to the right
+    hand[1, 35:55, 175:200] = False
+    hand[1, 30:60, 90:120] = True   # hole closed only diagonally (8-connected wall): still a hole
+    hand[1, 35:55, 95:115] = False
+    hand[1, 30, 90] = False
+    hand[2] = rng.random((96, 200)) < 0.62
+    hand[3, 10:80, 20:180] = True
+    hand[3, 20:70, 30:170] = rng.random((50, 140)) < 0.5  # dense debris inside a big hole
+    cases.append(hand)
+    for m in cases:
+        B, H, W = m.shape
+        bits = ops.pack(torch.from_numpy(m).cuda())
+        labels, counts, offsets = ops.label_bits(bits, W, connectivity=8)
+        table = ops.new_table(max(1, int(offsets[-1])), bits.device)
+        ops.region_table(labels, offsets, table, fg_bits=bits)
+        out, mask = ops.refine_labeled(bits, labels, table, offsets, min_size, W, want_mask=True)
+        got = ops.unpack(out, W, torch.bool).cpu().numpy()
+        for i in range(B):
+            want = ndi.binary_fill_holes(remove_small_objects(m[i], min_size=min_size, connectivity=2))
+            assert np.array_equal(got[i], want), (m.shape, i, np.argwhere(got[i] != want)[:5])
+        assert np.array_equal(mask.cpu().numpy().astype(bool), got)
