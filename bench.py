@@ -345,6 +345,7 @@ def run_b200(args):
         achieved = bpv * per_launch_vox / (avg_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "bytes_per_voxel": bpv, "avg_launch_ms": avg_ms, "launches": kcnt, "peak_source": peak_src, "kernel_time_share": shares,
+                "kernel_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
                 "timed": "per-kernel CUDA events on the launching stream over a second pass of the same K steps (eager launches)", "ms_per_step_with_events": ms_step_profiled}
     per_gpu = value / world * 1e6
     line = {

@@ -48,76 +48,6 @@ int pcs_ccl_ws_carve(void* ws, size_t ws_bytes, int B, int H, int W, int with_au
 }
 
 // ============================================================== kernels
-// thread per word: every run start becomes its own root
-template <class P>
-__global__ void __launch_bounds__(PCS_CCL_THREADS) k_ccl_init(P prov, int* __restrict__ parent, int B) {
-  const int H = prov.H, WW = prov.WW;
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)B * H * WW;
-  if (t >= total) return;
-  int k = (int)(t % WW);
-  int y = (int)((t / WW) % H);
-  long long b = t / ((long long)WW * H);
-  P p = prov.slice(b);
-  uint32_t F, S;
-  p.FS(y, k, F, S);
-  if (!S) return;
-  const int Wp = WW << 5;
-  int* par = parent + b * (long long)H * Wp;
-  int base = y * Wp + (k << 5);
-  while (S) {
-    int s = __ffs(S) - 1;
-    S &= S - 1;
-    par[base + s] = base + s;
-  }
-}
-
-// thread per word: unite each run with the runs it touches in the row above and
-// with the run it continues from the previous word
-template <class P, int CONN>
-__global__ void __launch_bounds__(PCS_CCL_THREADS) k_ccl_merge(P prov, int* __restrict__ parent, int B) {
-  const int H = prov.H, WW = prov.WW;
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)B * H * WW;
-  if (t >= total) return;
-  int k = (int)(t % WW);
-  int y = (int)((t / WW) % H);
-  long long b = t / ((long long)WW * H);
-  P p = prov.slice(b);
-  uint32_t F0, S0;
-  p.FS(y, k, F0, S0);
-  if (!F0) return;
-  PcsConnWords c;
-  p.conn(y, k, c);
-  const int Wp = WW << 5;
-  int* par = parent + b * (long long)H * Wp;
-  const int base = y * Wp + (k << 5);
-  if (c.J) {  // horizontal continuation across the word boundary
-    uint32_t Sl = p.Sword(y, k - 1);
-    int ls = 31 - __clz(Sl);
-    pcs_uf_union(par, base, base - 32 + ls);
-  }
-  if (y == 0) return;
-  if (!(c.U | c.UL | c.UR)) return;
-  uint32_t S = c.S;
-  const int abase = (y - 1) * Wp + (k << 5);
-  while (S) {
-    int s;
-    uint32_t R = pcs_pop_run(c.F, S, s);
-    // touch mask over the row above, bit i <-> x = 32k - 1 + i
-    unsigned long long T = ((unsigned long long)(c.U & R)) << 1;
-    if (CONN == 8) T |= (unsigned long long)(c.UL & R) | (((unsigned long long)(c.UR & R)) << 2);
-    while (T) {
-      int i = __ffsll((long long)T) - 1;
-      T &= T + (1ull << i);  // clear this run of consecutive touched pixels
-      int rel = (i - 1) >> 5;  // -1, 0, +1
-      int ja = (i - 1) & 31;
-      int sa = pcs_start_at_or_below(c.Sa[rel + 1], ja);
-      pcs_uf_union(par, base + s, abase + rel * 32 + sa);
-    }
-  }
-}
-
 // ---------------------------------------------------------------- tile-local union-find
 // CTA = CCL_TR rows x 32 words (1024 pixels).  Every run of the tile gets a slot in a shared
 // parent array (16 slots per word, ordered like the raster), unions between runs of the same
@@ -135,10 +65,12 @@ template <> struct PcsTile<PcsGenProv> { static constexpr int TR = 16, TW = 8, L
 
 __device__ __forceinline__ int pcs_lfind(volatile int* sp, int n) {
   int r = n, p = sp[r];
+  const int first = p;
   while (p != r) {
     r = p;
     p = sp[r];
   }
+  if (first != r) atomicMin((int*)sp + n, r);  // path compression (monotone, race-safe): later finds are one hop
   return r;
 }
 
@@ -299,10 +231,9 @@ template <class P, int CONN>
 __global__ void __launch_bounds__(PCS_CCL_THREADS) k_ccl_merge_edges(P prov, int* __restrict__ parent, int B, int per_slice) {
   const int H = prov.H, WW = prov.WW;
   constexpr int CCL_TR = PcsTile<P>::TR, TW = PcsTile<P>::TW;
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long long)B * per_slice) return;
-  const long long b = t / per_slice;
-  int e = (int)(t % per_slice);
+  int e = blockIdx.x * blockDim.x + threadIdx.x;  // edge word of the slice; the slice is blockIdx.y
+  if (e >= per_slice) return;
+  const long long b = blockIdx.y;
   const int ntop = (H + CCL_TR - 1) / CCL_TR;
   int y, k;
   if (e < ntop * WW) {
@@ -356,13 +287,12 @@ __global__ void __launch_bounds__(PCS_CCL_THREADS)
     k_ccl_flatten(P prov, int* __restrict__ parent, uint32_t* __restrict__ rootbits, int* __restrict__ chunk,
                   int* __restrict__ aux, int B, int CPR) {
   const int H = prov.H, WW = prov.WW;
-  long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int g32 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // 32-word chunk of the slice; the slice is blockIdx.y
   int lane = threadIdx.x & 31;
-  long long total = (long long)B * H * CPR;
-  if (g >= total) return;
-  int ch = (int)(g % CPR);
-  int y = (int)((g / CPR) % H);
-  long long b = g / ((long long)CPR * H);
+  if (g32 >= H * CPR) return;
+  const long long b = blockIdx.y;
+  const long long g = b * H * CPR + g32;
+  const int ch = g32 % CPR, y = g32 / CPR;
   int k = ch * 32 + lane;
   uint32_t roots = 0;
   if (k < WW) {
@@ -460,13 +390,12 @@ __global__ void __launch_bounds__(PCS_CCL_THREADS)
     k_ccl_rank(int* __restrict__ parent, const uint32_t* __restrict__ rootbits, const int* __restrict__ chunk,
                const int* __restrict__ offsets, long long* __restrict__ first_out, long long cap, int B, int H, int W,
                int WW, int CPR) {
-  long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int g32 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // 32-word chunk of the slice; the slice is blockIdx.y
   int lane = threadIdx.x & 31;
-  long long total = (long long)B * H * CPR;
-  if (g >= total) return;
-  int ch = (int)(g % CPR);
-  int y = (int)((g / CPR) % H);
-  long long b = g / ((long long)CPR * H);
+  if (g32 >= H * CPR) return;
+  const long long b = blockIdx.y;
+  const long long g = b * H * CPR + g32;
+  const int ch = g32 % CPR, y = g32 / CPR;
   int k = ch * 32 + lane;
   uint32_t roots = k < WW ? rootbits[(b * H + y) * (long long)WW + k] : 0u;
   int tot;
@@ -500,15 +429,15 @@ __global__ void __launch_bounds__(PCS_CCL_THREADS)
     k_ccl_relabel(P prov, const int* __restrict__ parent, OutT* __restrict__ out, int B, int CPR) {
   __shared__ int lab[PCS_CCL_THREADS / 32][32][33];
   const int H = prov.H, WW = prov.WW, W = prov.W;
-  long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int g32 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // 32-word chunk of the slice; the slice is blockIdx.y
   int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
-  long long total = (long long)B * H * CPR;
-  if (g >= total) return;
-  int ch = (int)(g % CPR);
-  int y = (int)((g / CPR) % H);
-  long long b = g / ((long long)CPR * H);
+  if (g32 >= H * CPR) return;
+  const long long b = blockIdx.y;
+  const long long g = b * H * CPR + g32;
+  const int ch = g32 % CPR, y = g32 / CPR;
   int k = ch * 32 + lane;
   uint32_t F = 0, S = 0;
+  int one = 0;  // label of the word's only run (words with several runs go through shared memory)
   const int Wp = WW << 5;
   const int* par = parent + b * (long long)H * Wp;
   if (k < WW) {
@@ -516,6 +445,11 @@ __global__ void __launch_bounds__(PCS_CCL_THREADS)
     p.FS(y, k, F, S);
     int base = y * Wp + (k << 5);
     uint32_t rem = S;
+    if (rem && !(rem & (rem - 1))) {
+      const int p0 = par[base + __ffs(rem) - 1];
+      one = p0 < 0 ? -p0 : -par[p0];
+      rem = 0;
+    }
     while (rem) {  // four independent lookups in flight per iteration
       int s0 = __ffs(rem) - 1;
       rem &= rem - 1;
@@ -542,20 +476,35 @@ __global__ void __launch_bounds__(PCS_CCL_THREADS)
   __syncwarp();
   OutT* orow = out + (b * H + y) * (long long)W;
   int nk = min(32, WW - ch * 32);
-  if (sizeof(OutT) == 4 && (W & 3) == 0) {
+  if (__ballot_sync(0xffffffffu, F != 0u) == 0u && sizeof(OutT) == 4 && (W & 3) == 0) {
+    // no foreground in these 32 words: plain zero fill
+    for (int k4 = 0; k4 < nk; k4 += 4) {
+      const int kk = k4 + (lane >> 3);
+      const int x = ((ch * 32 + kk) << 5) + ((lane & 7) << 2);
+      if (kk < nk && x < W) *reinterpret_cast<int4*>(orow + x) = make_int4(0, 0, 0, 0);
+    }
+  } else if (sizeof(OutT) == 4 && (W & 3) == 0) {
     // 16-byte stores: a lane owns 4 consecutive pixels, 4 words (128 pixels) per iteration
     const int sub = lane >> 3, nib = (lane & 7) << 2;
     for (int k4 = 0; k4 < nk; k4 += 4) {
       const int kk = k4 + sub;
-      uint32_t f = __shfl_sync(0xffffffffu, F, kk & 31);
-      uint32_t s = __shfl_sync(0xffffffffu, S, kk & 31);
+      const uint32_t f = __shfl_sync(0xffffffffu, F, kk & 31);
+      const uint32_t s = __shfl_sync(0xffffffffu, S, kk & 31);
+      const int l1 = __shfl_sync(0xffffffffu, one, kk & 31);
       int4 v = make_int4(0, 0, 0, 0);
       const uint32_t n = kk < nk ? (f >> nib) & 0xfu : 0u;
       if (n) {
-        if (n & 1u) v.x = lab[wl][kk][pcs_start_at_or_below(s, nib)];
-        if (n & 2u) v.y = lab[wl][kk][pcs_start_at_or_below(s, nib + 1)];
-        if (n & 4u) v.z = lab[wl][kk][pcs_start_at_or_below(s, nib + 2)];
-        if (n & 8u) v.w = lab[wl][kk][pcs_start_at_or_below(s, nib + 3)];
+        if (l1) {  // single-run word: every foreground pixel carries the same label
+          v.x = (n & 1u) ? l1 : 0;
+          v.y = (n & 2u) ? l1 : 0;
+          v.z = (n & 4u) ? l1 : 0;
+          v.w = (n & 8u) ? l1 : 0;
+        } else {
+          if (n & 1u) v.x = lab[wl][kk][pcs_start_at_or_below(s, nib)];
+          if (n & 2u) v.y = lab[wl][kk][pcs_start_at_or_below(s, nib + 1)];
+          if (n & 4u) v.z = lab[wl][kk][pcs_start_at_or_below(s, nib + 2)];
+          if (n & 8u) v.w = lab[wl][kk][pcs_start_at_or_below(s, nib + 3)];
+        }
       }
       const int x = ((ch * 32 + kk) << 5) + nib;
       if (kk < nk && x < W) *reinterpret_cast<int4*>(orow + x) = v;  // W % 4 == 0: x + 3 < W too
@@ -564,9 +513,10 @@ __global__ void __launch_bounds__(PCS_CCL_THREADS)
     for (int kk = 0; kk < nk; ++kk) {
       uint32_t f = __shfl_sync(0xffffffffu, F, kk);
       uint32_t s = __shfl_sync(0xffffffffu, S, kk);
+      const int l1 = __shfl_sync(0xffffffffu, one, kk);
       int x = ((ch * 32 + kk) << 5) + lane;
       int v = 0;
-      if ((f >> lane) & 1u) v = lab[wl][kk][pcs_start_at_or_below(s, lane)];
+      if ((f >> lane) & 1u) v = l1 ? l1 : lab[wl][kk][pcs_start_at_or_below(s, lane)];
       if (x < W) orow[x] = (OutT)v;
     }
   }
@@ -579,12 +529,11 @@ template <class P>
 __global__ void __launch_bounds__(PCS_CCL_THREADS)
     k_ccl_mark(P prov, int* __restrict__ parent, const uint32_t* __restrict__ m, int mode, int B) {
   const int H = prov.H, WW = prov.WW, W = prov.W;
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)B * H * WW;
-  if (t >= total) return;
-  int k = (int)(t % WW);
-  int y = (int)((t / WW) % H);
-  long long b = t / ((long long)WW * H);
+  const int t32 = blockIdx.x * blockDim.x + threadIdx.x;  // word of the slice; the slice is blockIdx.y
+  if (t32 >= H * WW) return;
+  const long long b = blockIdx.y;
+  const long long t = b * H * WW + t32;
+  const int k = t32 % WW, y = t32 / WW;
   P p = prov.slice(b);
   uint32_t F, S;
   p.FS(y, k, F, S);
@@ -617,12 +566,11 @@ __global__ void __launch_bounds__(PCS_CCL_THREADS)
 template <class P>
 __global__ void __launch_bounds__(PCS_CCL_THREADS) k_ccl_area(P prov, const int* __restrict__ parent, int* __restrict__ aux, int B) {
   const int H = prov.H, WW = prov.WW;
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)B * H * WW;
-  if (t >= total) return;
-  int k = (int)(t % WW);
-  int y = (int)((t / WW) % H);
-  long long b = t / ((long long)WW * H);
+  const int t32 = blockIdx.x * blockDim.x + threadIdx.x;  // word of the slice; the slice is blockIdx.y
+  if (t32 >= H * WW) return;
+  const long long b = blockIdx.y;
+  const long long t = b * H * WW + t32;
+  const int k = t32 % WW, y = t32 / WW;
   P p = prov.slice(b);
   uint32_t F, S;
   p.FS(y, k, F, S);
@@ -642,14 +590,13 @@ __global__ void __launch_bounds__(PCS_CCL_THREADS) k_ccl_area(P prov, const int*
 __global__ void __launch_bounds__(PCS_CCL_THREADS)
     k_ccl_mark_small(int* __restrict__ parent, const uint32_t* __restrict__ rootbits, const int* __restrict__ aux,
                      int min_size, int B, int H, int WW) {
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)B * H * WW;
-  if (t >= total) return;
+  const int t32 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t32 >= H * WW) return;
+  const long long b = blockIdx.y;
+  const long long t = b * H * WW + t32;
   uint32_t roots = rootbits[t];
   if (!roots) return;
-  int k = (int)(t % WW);
-  int y = (int)((t / WW) % H);
-  long long b = t / ((long long)WW * H);
+  const int k = t32 % WW, y = t32 / WW;
   const int Wp = WW << 5;
   long long sb = b * (long long)H * Wp;
   int base = y * Wp + (k << 5);
@@ -667,12 +614,11 @@ __global__ void __launch_bounds__(PCS_CCL_THREADS)
     k_ccl_select(P prov, const int* __restrict__ parent, int want_marked, const uint32_t* __restrict__ or_bits,
                  const int32_t* __restrict__ veto_counts, uint32_t* __restrict__ out, uint8_t* __restrict__ mask, int B) {
   const int H = prov.H, WW = prov.WW;
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)B * H * WW;
-  if (t >= total) return;
-  int k = (int)(t % WW);
-  int y = (int)((t / WW) % H);
-  long long b = t / ((long long)WW * H);
+  const int t32 = blockIdx.x * blockDim.x + threadIdx.x;  // word of the slice; the slice is blockIdx.y
+  if (t32 >= H * WW) return;
+  const long long b = blockIdx.y;
+  const long long t = b * H * WW + t32;
+  const int k = t32 % WW, y = t32 / WW;
   P p = prov.slice(b);
   uint32_t F, S;
   p.FS(y, k, F, S);
@@ -732,11 +678,10 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     k_hole_candidates(const uint32_t* __restrict__ fbits, const uint32_t* __restrict__ bb, uint32_t* __restrict__ cand,
                       uint32_t* __restrict__ seed, int B, int H, int W, int WW) {
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)B * H * WW;
-  if (t >= total) return;
-  const int k = (int)(t % WW);
-  const int y = (int)((t / WW) % H);
+  const int t32 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t32 >= H * WW) return;
+  const long long t = (long long)blockIdx.y * H * WW + t32;
+  const int k = t32 % WW, y = t32 / WW;
   const uint32_t vm = pcs_valid_mask(k, W);
   const uint32_t box = bb[t];
   const uint32_t C = ~fbits[t] & box & vm;
@@ -898,14 +843,13 @@ __global__ void __launch_bounds__(REFINE_MAX_WARPS * 32)
 __global__ void __launch_bounds__(256)
     k_hole_seeds(const uint32_t* __restrict__ kept, const uint32_t* __restrict__ cand, uint32_t* __restrict__ seed, int B, int H,
                  int W, int WW) {
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)B * H * WW;
-  if (t >= total) return;
+  const int t32 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t32 >= H * WW) return;
+  const long long t = (long long)blockIdx.y * H * WW + t32;
   const uint32_t C = cand[t];
   uint32_t M = 0;
   if (C) {
-    const int k = (int)(t % WW);
-    const int y = (int)((t / WW) % H);
+    const int k = t32 % WW, y = t32 / WW;
     auto open_at = [&](long long idx, int kk) { return ~kept[idx] & ~cand[idx] & pcs_valid_mask(kk, W); };
     const uint32_t n_c = open_at(t, k);
     uint32_t adj = (n_c << 1) | (n_c >> 1);
@@ -924,16 +868,14 @@ template <class P>
 static int ccl_forest(const P& prov, int B, int conn, const PcsCclWs& ws, int32_t* counts, int zero_aux, cudaStream_t st) {
   const int H = prov.H, WW = prov.WW;
   const int CPR = (WW + 31) / 32;
-  long long words = (long long)B * H * WW;
-  long long warps = (long long)B * H * CPR;
-  unsigned gw = pcs_blocks(words, PCS_CCL_THREADS);
-  unsigned gc = pcs_blocks(warps * 32, PCS_CCL_THREADS);
+  dim3 gw(pcs_blocks((long long)H * WW, PCS_CCL_THREADS), B);
+  dim3 gc(pcs_blocks((long long)H * CPR * 32, PCS_CCL_THREADS), B);
   constexpr int CCL_TR = PcsTile<P>::TR, TW = PcsTile<P>::TW;
   PCS_REQUIRE(B <= 65535 && (H + CCL_TR - 1) / CCL_TR <= 65535, "grid too large for the tile kernel");
   dim3 gt((WW + TW - 1) / TW, (H + CCL_TR - 1) / CCL_TR, B);
   const int ntop = (H + CCL_TR - 1) / CCL_TR;
   const int per_slice = ntop * WW + (H - ntop) * 2 * ((WW + TW - 1) / TW);  // tile-edge words of one slice
-  unsigned ge = pcs_blocks((long long)B * per_slice, PCS_CCL_THREADS);
+  dim3 ge(pcs_blocks(per_slice, PCS_CCL_THREADS), B);
   if (conn == 8) {
     PCS_LAUNCH("k_ccl_tile", st, (k_ccl_tile<P, 8><<<gt, CCL_TILE_THREADS, 0, st>>>(prov, ws.parent)));
     PCS_LAUNCH("k_ccl_merge_edges", st, (k_ccl_merge_edges<P, 8><<<ge, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, B, per_slice)));
@@ -961,7 +903,7 @@ static int ccl_label(const P& prov, int B, int conn, void* labels, int label_byt
   rc = ccl_forest(prov, B, conn, ws, counts, 0, st);
   if (rc) return rc;
   const int H = prov.H, WW = prov.WW, CPR = (WW + 31) / 32;
-  unsigned gc = pcs_blocks((long long)B * H * CPR * 32, PCS_CCL_THREADS);
+  dim3 gc(pcs_blocks((long long)H * CPR * 32, PCS_CCL_THREADS), B);
   PCS_LAUNCH("k_ccl_rank", st, k_ccl_rank<<<gc, PCS_CCL_THREADS, 0, st>>>(ws.parent, ws.rootbits, ws.chunk, ws.offsets, first_out, cap, B, H, prov.W, WW, CPR));
   if (label_bytes == 4)
     PCS_LAUNCH("k_ccl_relabel", st, k_ccl_relabel<P, int32_t><<<gc, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, (int32_t*)labels, B, CPR));
@@ -974,6 +916,7 @@ static int ccl_label(const P& prov, int B, int conn, void* labels, int label_byt
 static int check_dims(int B, int H, int W) {
   PCS_REQUIRE(B >= 1 && H >= 1 && W >= 1, "empty batch or image");
   PCS_REQUIRE(H <= 16384 && W <= 16384, "image side above 16384 is not supported");
+  PCS_REQUIRE(B <= 65535, "batch above 65535 slices");
   return PCS_OK;
 }
 
@@ -1011,7 +954,7 @@ int pcs_fill_holes_bits(const uint32_t* bits, uint32_t* out, int B, int H, int W
   PcsBinProv prov{bits, H, W, pcs_words(W), 1};  // background, 4-connected (tiff_analysis.py:880)
   rc = ccl_forest(prov, B, 4, ws, nullptr, 0, st);
   if (rc) return rc;
-  unsigned gw = pcs_blocks((long long)B * H * prov.WW, PCS_CCL_THREADS);
+  dim3 gw(pcs_blocks((long long)H * prov.WW, PCS_CCL_THREADS), B);
   PCS_LAUNCH("k_ccl_mark", st, k_ccl_mark<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, nullptr, 0, B));
   PCS_LAUNCH("k_ccl_select", st, k_ccl_select<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, 0, bits, nullptr, out, nullptr, B));
   return pcs_check_launch("fill holes");
@@ -1039,7 +982,7 @@ int pcs_fill_holes_table_bits(const uint32_t* bits, const int64_t* table, int64_
   uint32_t* seed = (uint32_t*)(extra + 2 * plane);
   cudaMemsetAsync(bb, 0, (size_t)B * H * WW * 4, st);
   PCS_LAUNCH("k_bbox_raster", st, k_bbox_raster<<<pcs_blocks(cap * 32, 256), 256, 0, st>>>((const long long*)table, cap, offsets, min_size, bb, B, H, WW));
-  unsigned gw = pcs_blocks((long long)B * H * WW, PCS_CCL_THREADS);
+  dim3 gw(pcs_blocks((long long)H * WW, PCS_CCL_THREADS), B);
   PCS_LAUNCH("k_hole_candidates", st, k_hole_candidates<<<gw, 256, 0, st>>>(bits, bb, cand, seed, B, H, W, WW));
   PcsBinProv prov{cand, H, W, WW, 0};
   rc = ccl_forest(prov, B, 4, ws, nullptr, 0, st);
@@ -1082,7 +1025,7 @@ int pcs_refine_labeled_bits(const uint32_t* bits, const int32_t* labels, const i
   }
   PCS_LAUNCH("k_refine_rows", st, (k_refine_rows<<<pcs_blocks(rows, warps), warps * 32, warps * warp_bytes, st>>>(
       bits, labels, (const long long*)table, cap, offsets, min_size, kept, cand, rows, H, W, WW)));
-  unsigned gw = pcs_blocks((long long)B * H * WW, PCS_CCL_THREADS);
+  dim3 gw(pcs_blocks((long long)H * WW, PCS_CCL_THREADS), B);
   PCS_LAUNCH("k_hole_seeds", st, (k_hole_seeds<<<gw, 256, 0, st>>>(kept, cand, seed, B, H, W, WW)));
   PcsBinProv prov{cand, H, W, WW, 0};
   rc = ccl_forest(prov, B, 4, ws, nullptr, 0, st);
@@ -1108,7 +1051,7 @@ int pcs_remove_small_bits(const uint32_t* bits, uint32_t* out, int B, int H, int
   PcsBinProv prov{bits, H, W, pcs_words(W), 0};
   rc = ccl_forest(prov, B, connectivity, ws, nullptr, 1, st);
   if (rc) return rc;
-  unsigned gw = pcs_blocks((long long)B * H * prov.WW, PCS_CCL_THREADS);
+  dim3 gw(pcs_blocks((long long)H * prov.WW, PCS_CCL_THREADS), B);
   PCS_LAUNCH("k_ccl_area", st, k_ccl_area<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, ws.aux, B));
   PCS_LAUNCH("k_ccl_mark_small", st, k_ccl_mark_small<<<gw, PCS_CCL_THREADS, 0, st>>>(ws.parent, ws.rootbits, ws.aux, min_size, B, H, prov.WW));
   PCS_LAUNCH("k_ccl_select", st, k_ccl_select<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, 0, nullptr, nullptr, out, nullptr, B));
@@ -1127,7 +1070,7 @@ int pcs_select_components_bits(const uint32_t* bits, const uint32_t* seeds, uint
   PcsBinProv prov{bits, H, W, pcs_words(W), 0};
   rc = ccl_forest(prov, B, connectivity, ws, nullptr, 0, st);
   if (rc) return rc;
-  unsigned gw = pcs_blocks((long long)B * H * prov.WW, PCS_CCL_THREADS);
+  dim3 gw(pcs_blocks((long long)H * prov.WW, PCS_CCL_THREADS), B);
   PCS_LAUNCH("k_ccl_mark", st, k_ccl_mark<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, seeds, 1, B));
   PCS_LAUNCH("k_ccl_select", st, k_ccl_select<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, 1, nullptr, nullptr, out, nullptr, B));
   return pcs_check_launch("select components");
@@ -1146,7 +1089,7 @@ int pcs_local_maxima_conn(const uint32_t* planes, const uint32_t* higher, uint32
   PcsGenProv prov{planes, (long long)B * H * pcs_words(W), H, W, pcs_words(W)};
   rc = ccl_forest(prov, B, connectivity, ws, counts, 0, st);
   if (rc) return rc;
-  unsigned gw = pcs_blocks((long long)B * H * prov.WW, PCS_CCL_THREADS);
+  dim3 gw(pcs_blocks((long long)H * prov.WW, PCS_CCL_THREADS), B);
   PCS_LAUNCH("k_ccl_mark", st, k_ccl_mark<PcsGenProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, higher, 1, B));
   // a plateau that is the whole image (counts == 1) is not a maximum
   PCS_LAUNCH("k_ccl_select", st, k_ccl_select<PcsGenProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, 0, nullptr, counts, out, nullptr, B));

@@ -55,6 +55,22 @@ __device__ __forceinline__ uint32_t pcs_valid_mask(int k, int W) {
 }
 
 __device__ __forceinline__ int pcs_ld_cg(const int* p) { return __ldcg(p); }
+// t = (i2 * n1 + i1) * n0 + i0 with 32-bit divisions whenever t fits (64-bit division by a
+// run-time value costs ~100 instructions, which dominated the word-parallel kernels)
+__device__ __forceinline__ void pcs_split3(long long t, int n0, int n1, int& i0, int& i1, long long& i2) {
+  if (t <= 0xffffffffLL) {
+    const unsigned u = (unsigned)t, q = u / (unsigned)n0, q2 = q / (unsigned)n1;
+    i0 = (int)(u - q * (unsigned)n0);
+    i1 = (int)(q - q2 * (unsigned)n1);
+    i2 = q2;
+  } else {
+    const long long q = t / n0, q2 = q / n1;
+    i0 = (int)(t - q * n0);
+    i1 = (int)(q - q2 * n1);
+    i2 = q2;
+  }
+}
+
 
 // start bit of the within-word run of `w` that contains bit j (bit j must be set)
 __device__ __forceinline__ int pcs_run_start(uint32_t w, int j) {

@@ -45,9 +45,9 @@ __global__ void __launch_bounds__(256)
   const int lane = threadIdx.x & 31;
   long long total = (long long)B * NB * WW;
   if (g >= total) return;
-  const int k = (int)(g % WW);
-  const int q = (int)((g / WW) % NB);
-  const long long b = g / ((long long)WW * NB);
+  int k, q;
+  long long b;
+  pcs_split3(g, WW, NB, k, q, b);
   const int y = (q << 5) + lane;
   uint32_t w = 0xffffffffu;  // rows past the image never act as background
   if (y < H) {
@@ -184,7 +184,21 @@ __global__ void __launch_bounds__(EDT_TW)
   const long long band = (b * NB + q) * (long long)Wp;
   const int rows = min(32, H - (q << 5));
   const int cols = min(EDT_TW, W - x0);
-  // background pixels have g = 0 and distance 0: clear both tiles, then visit only the foreground
+  // column words and carries of both column slots of this thread are requested first, so one
+  // global round trip is in flight while the tiles are cleared (background: g = 0, distance 0)
+  const int xa = x0 - EDT_HALO + tid, xb = xa + EDT_TW;
+  const bool ina = xa >= 0 && xa < W, inb = tid < 2 * EDT_HALO && xb < W;  // xb >= 0 always
+  uint32_t fa = 0, fb = 0, cua = 0, cda = 0, cub = 0, cdb = 0;
+  if (ina) {
+    fa = __ldg(vw + band + xa);  // set bits = foreground rows of this column
+    cua = __ldg(up + band + xa);
+    cda = __ldg(dn + band + xa);
+  }
+  if (inb) {
+    fb = __ldg(vw + band + xb);
+    cub = __ldg(up + band + xb);
+    cdb = __ldg(dn + band + xb);
+  }
   {
     uint4* gz = reinterpret_cast<uint4*>(&g[0][0]);
     for (int i = tid; i < 32 * EDT_TWH / 16; i += EDT_TW) gz[i] = make_uint4(0, 0, 0, 0);
@@ -195,14 +209,15 @@ __global__ void __launch_bounds__(EDT_TW)
   // pass 1: vertical distances of the foreground pixels; the tile's own foreground pixels are also
   // appended to a work list so that pass 2 spreads them evenly over the CTA (a thread per pixel,
   // not a thread per column: columns through a particle would serialise ~20 searches)
-  for (int col = tid; col < EDT_TWH; col += EDT_TW) {
-    const int x = x0 - EDT_HALO + col;
-    uint32_t f = 0;
-    if (x >= 0 && x < W) {
-      f = __ldg(vw + band + x);  // set bits = foreground rows of this column
+#pragma unroll
+  for (int slot = 0; slot < 2; ++slot) {
+    if (slot == 1 && tid >= 2 * EDT_HALO) break;
+    const int col = tid + slot * EDT_TW;
+    const int x = slot ? xb : xa;
+    uint32_t f = slot ? fb : fa;
+    if (slot ? inb : ina) {
       if (f) {
-        const uint32_t z = ~f;
-        const uint32_t cu = __ldg(up + band + x), cd = __ldg(dn + band + x);
+        const uint32_t z = ~f, cu = slot ? cub : cua, cd = slot ? cdb : cda;
         uint32_t ff = f;
         while (ff) {
           const int r = __ffs(ff) - 1;

@@ -25,9 +25,9 @@ __global__ void __launch_bounds__(MORPH_THREADS)
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)B * H * WW;
   if (t >= total) return;
-  const int k = (int)(t % WW);
-  const int y = (int)((t / WW) % H);
-  const long long b = t / ((long long)WW * H);
+  int k, y;
+  long long b;
+  pcs_split3(t, WW, H, k, y, b);
   const uint32_t* src = in + b * (long long)H * WW;
   const uint32_t bw = border ? 0xffffffffu : 0u;
   uint32_t acc = 0;
@@ -104,9 +104,9 @@ __global__ void __launch_bounds__(MORPH_THREADS)
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)B * H * WW;
   if (t >= total) return;
-  const int k = (int)(t % WW);
-  const int y = (int)((t / WW) % H);
-  const long long b = t / ((long long)WW * H);
+  int k, y;
+  long long b;
+  pcs_split3(t, WW, H, k, y, b);
   const uint32_t* src = in + b * (long long)H * WW;
   const int r = size >> 1;
   const int need = (size * size) / 2 + 1;  // ones needed for the median to be 1
@@ -142,9 +142,9 @@ __global__ void __launch_bounds__(MORPH_THREADS)
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)B * strips * WW;
   if (t >= total) return;
-  const int k = (int)(t % WW);
-  const int strip = (int)((t / WW) % strips);
-  const long long b = t / ((long long)WW * strips);
+  int k, strip;
+  long long b;
+  pcs_split3(t, WW, strips, k, strip, b);
   const uint32_t* src = in + b * (long long)H * WW;
   const int y0 = strip * MAJ_ROWS;
   const uint32_t vm = pcs_valid_mask(k, W);

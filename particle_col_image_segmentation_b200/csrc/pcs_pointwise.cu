@@ -42,8 +42,10 @@ __device__ __forceinline__ uint32_t pcs_pack_word(const T* __restrict__ row, int
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; \
   long long total = (long long)B * H * WW;                        \
   if (t >= total) return;                                         \
-  int k = (int)(t % WW);                                          \
-  long long rowi = t / WW; /* b*H + y */
+  int k, y_;                                                      \
+  long long b_;                                                   \
+  pcs_split3(t, WW, H, k, y_, b_);                                \
+  long long rowi = b_ * H + y_; /* b*H + y */
 
 // cmp: 0 '>', 1 '>=', 2 '<', 3 '<=', 4 '==', 5 '!='
 template <typename T, typename TT>

@@ -80,9 +80,9 @@ __global__ void __launch_bounds__(PROPS_THREADS)
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)B * strips * WW;
   if (t >= total) return;
-  const int k = (int)(t % WW);
-  const int strip = (int)((t / WW) % strips);
-  const long long b = t / ((long long)WW * strips);
+  int k, strip;
+  long long b;
+  pcs_split3(t, WW, strips, k, strip, b);
   const long long base = offsets ? (long long)offsets[b] : 0;
   const int x0 = k << 5;
   const int n = min(32, W - x0);
@@ -186,25 +186,40 @@ __global__ void __launch_bounds__(PROPS_THREADS)
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)B * strips * WW;
   if (t >= total) return;
-  const int k = (int)(t % WW);
-  const int strip = (int)((t / WW) % strips);
-  const long long b = t / ((long long)WW * strips);
+  int k, strip;
+  long long b;
+  pcs_split3(t, WW, strips, k, strip, b);
   const long long base = offsets ? (long long)offsets[b] : 0;
   const int x0 = k << 5;
   const bool has_int = intensity != nullptr, has_ov = ov_bits != nullptr;
+  // rows start 16-byte aligned and the word is complete: vector loads of the intensities
+  const bool vec = has_int && x0 + 32 <= W && ((W * sizeof(IntT)) & 15) == 0 && (((uintptr_t)intensity) & 15) == 0;
   const int y0 = strip * PROPS_ROWS;
-  uint32_t fw[PROPS_ROWS];
-#pragma unroll
-  for (int r = 0; r < PROPS_ROWS; ++r) fw[r] = (y0 + r < H) ? __ldg(fg_bits + (b * H + y0 + r) * (long long)WW + k) : 0u;
   RegionAcc acc;
   acc.label = 0;
-#pragma unroll
+  const uint32_t* fcol = fg_bits + (b * H + y0) * (long long)WW + k;
+  uint32_t fnext = __ldg(fcol);  // y0 < H always; the next row's word is requested one iteration ahead
+#pragma unroll 1
   for (int r = 0; r < PROPS_ROWS; ++r) {
-    uint32_t f = fw[r];
+    const uint32_t f = fnext;
+    fnext = (r + 1 < PROPS_ROWS && y0 + r + 1 < H) ? __ldg(fcol + (long long)(r + 1) * WW) : 0u;
     if (f == 0u) continue;
     const int y = y0 + r;
     const long long rowo = (b * H + y) * (long long)W + x0;
     const uint32_t ovw = has_ov ? ov_bits[(b * H + y) * (long long)WW + k] : 0u;
+    // the 32 intensities of the word in one go (16-byte loads) when the row allows it
+    constexpr int NW = 8 * (int)sizeof(IntT);  // 32-bit registers holding the word's pixels
+    uint32_t iw[NW];
+    if (has_int && vec) {
+#pragma unroll
+      for (int v = 0; v < NW / 4; ++v) {
+        const uint4 q4 = __ldg(reinterpret_cast<const uint4*>(intensity + rowo) + v);
+        iw[4 * v] = q4.x;
+        iw[4 * v + 1] = q4.y;
+        iw[4 * v + 2] = q4.z;
+        iw[4 * v + 3] = q4.w;
+      }
+    }
     uint32_t S = f & ~(f << 1);
     while (S) {
       const int s = __ffs(S) - 1;
@@ -214,8 +229,21 @@ __global__ void __launch_bounds__(PROPS_THREADS)
       const int lab = labels[rowo + s];
       const int xs = x0 + s;
       long long si = 0;
-      if (has_int)
-        for (int i = 0; i < len; ++i) si += (long long)intensity[rowo + s + i];
+      if (has_int) {
+        if (vec) {
+          const uint32_t rm = (len >= 32 ? 0xffffffffu : ((1u << len) - 1u)) << s;
+          uint32_t sum = 0;  // 32 pixels of at most 16 bits: no overflow
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const uint32_t px = sizeof(IntT) == 2 ? ((i & 1) ? (iw[i >> 1] >> 16) : (iw[i >> 1] & 0xffffu))
+                                                  : ((iw[i >> 2] >> (8 * (i & 3))) & 0xffu);
+            sum += (rm >> i) & 1u ? px : 0u;
+          }
+          si = sum;
+        } else {
+          for (int i = 0; i < len; ++i) si += (long long)intensity[rowo + s + i];
+        }
+      }
       if (lab != acc.label) {
         acc_flush(acc, table, cap, base, has_int, has_ov);
         acc.label = lab;
@@ -251,9 +279,10 @@ __global__ void __launch_bounds__(256)
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)B * H * WW;
   if (t >= total) return;
-  const int k = (int)(t % WW);
-  const long long rowi = t / WW;
-  const long long b = rowi / H;
+  int k, y_;
+  long long b;
+  pcs_split3(t, WW, H, k, y_, b);
+  const long long rowi = b * H + y_;
   const LabT* lrow = labels + rowi * (long long)W + (k << 5);
   const uint8_t* kp = keep + b * lut_stride;
   const int n = min(32, W - (k << 5));
@@ -284,9 +313,10 @@ __global__ void __launch_bounds__(256)
     out[t] = 0u;
     return;
   }
-  const int k = (int)(t % WW);
-  const long long rowi = t / WW;
-  const long long b = rowi / H;
+  int k, y_;
+  long long b;
+  pcs_split3(t, WW, H, k, y_, b);
+  const long long rowi = b * H + y_;
   const int32_t* lrow = labels + rowi * (long long)W + (k << 5);
   const long long base = offsets[b];
   uint32_t o = 0, S = f & ~(f << 1);
