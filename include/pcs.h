@@ -146,6 +146,11 @@ int pcs_edt_bits(const uint32_t* bits, int invert, int B, int H, int W, double* 
 int pcs_table_init(int64_t* table, int64_t cap, void* stream);
 int pcs_region_table(const void* labels, int label_bytes, const void* intensity, int intensity_dtype, const uint32_t* fg_bits,
                      const uint32_t* ov_bits, const int32_t* offsets, int64_t* table, int64_t cap, int B, int H, int W, void* stream);
+/* the float64 table the callers consume, row-major double[cap][13], rows [0, offsets[B]) filled:
+ * z (= z0 + slice), label, area, centroid_y, centroid_x, min_row, min_col, max_row + 1, max_col + 1,
+ * first_row, first_col, intensity_sum, intensity_mean (regionprops .area/.centroid/.bbox/.coords[0],
+ * tiff_analysis.py:754-773; exact integer sums, one IEEE division each) */
+int pcs_table_finalize(const int64_t* table, int64_t cap, const int32_t* offsets, int B, int W, double z0, double* out, void* stream);
 /* pixels whose label has keep[b][label] != 0 (merged_image |= labels == v, tiff_analysis.py:878) */
 int pcs_select_labels(const void* labels, int label_bytes, const uint8_t* keep, int64_t lut_stride, uint32_t* out, int B, int H, int W, void* stream);
 /* pixels whose component area >= min_size, from the table (tiff_analysis.py:769-773) */
@@ -166,7 +171,8 @@ int pcs_min_dist_f64(const double* a, int64_t na, const double* b, int64_t nb, d
 size_t pcs_segment_workspace_bytes(int B, int H, int W);
 int pcs_segment_chunk(const uint16_t* img, int B, int H, int W, int denoise_size, int min_size, uint8_t* mask, int32_t* labels,
                       uint8_t* refined, double* edt, int32_t* thr, int32_t* counts, int32_t* offsets, int64_t* table,
-                      int64_t cap, void* ws, size_t ws_bytes, void* stream);
+                      int64_t cap, double* ftable /* optional double[cap][13], see pcs_table_finalize */, int z0, void* ws,
+                      size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

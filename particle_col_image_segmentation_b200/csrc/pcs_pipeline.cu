@@ -48,7 +48,7 @@ size_t pcs_segment_workspace_bytes(int B, int H, int W) { return seg_carve(nullp
 
 int pcs_segment_chunk(const uint16_t* img, int B, int H, int W, int denoise_size, int min_size, uint8_t* mask, int32_t* labels,
                       uint8_t* refined, double* edt, int32_t* thr, int32_t* counts, int32_t* offsets, int64_t* table,
-                      int64_t cap, void* ws, size_t ws_bytes, void* stream) {
+                      int64_t cap, double* ftable, int z0, void* ws, size_t ws_bytes, void* stream) {
   PCS_REQUIRE(B >= 1 && H >= 1 && W >= 1, "empty batch or image");
   PCS_REQUIRE(img && mask && labels && refined && edt && thr && counts && offsets && table, "null argument");
   if (ws == nullptr || ws_bytes < pcs_segment_workspace_bytes(B, H, W)) {
@@ -73,6 +73,7 @@ int pcs_segment_chunk(const uint16_t* img, int B, int H, int W, int denoise_size
   STEP(pcs_label_bits(bits, B, H, W, 8, 0, labels, 4, counts, offsets, nullptr, 0, w.ccl, w.ccl_bytes, stream));
   STEP(pcs_table_init(table, cap, stream));
   STEP(pcs_region_table(labels, 4, img, 1, bits, nullptr, offsets, table, cap, B, H, W, stream));
+  if (ftable) STEP(pcs_table_finalize(table, cap, offsets, B, W, (double)z0, ftable, stream));
   // small objects out and holes filled in one call: areas come from the table just built, and only
   // row gaps between two runs of one label can hold hole pixels
   STEP(pcs_refine_labeled_bits(bits, labels, table, cap, offsets, min_size > 1 ? min_size : 1, w.refined, refined, B, H, W, w.ccl, w.ccl_bytes, stream));

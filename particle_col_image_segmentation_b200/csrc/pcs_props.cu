@@ -271,6 +271,40 @@ __global__ void __launch_bounds__(PROPS_THREADS)
   acc_flush(acc, table, cap, base, has_int, has_ov);
 }
 
+// thread per table row: the float64 table the callers consume (same columns and arithmetic as
+// oracle/pipeline.py::region_table -- exact integer sums, one IEEE division for centroid and mean):
+//   z, label, area, centroid_y, centroid_x, min_row, min_col, max_row + 1, max_col + 1,
+//   first_row, first_col, intensity_sum, intensity_mean
+__global__ void __launch_bounds__(256)
+    k_table_finalize(const long long* __restrict__ table, long long cap, const int* __restrict__ offsets, int B, int W, double z0,
+                     double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n = min((long long)offsets[B], cap);
+  if (i >= n) return;
+  int lo = 0, hi = B;  // slice of this row: offsets[lo] <= i < offsets[lo + 1]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if ((long long)offsets[mid] <= i) lo = mid; else hi = mid;
+  }
+  const double area = (double)table[T_AREA * cap + i];
+  const long long first = table[T_FIRST * cap + i];
+  const double si = (double)table[T_SUMI * cap + i];
+  double* o = out + i * 13;
+  o[0] = z0 + (double)lo;
+  o[1] = (double)(i - offsets[lo] + 1);
+  o[2] = area;
+  o[3] = __ddiv_rn((double)table[T_SUMY * cap + i], area);
+  o[4] = __ddiv_rn((double)table[T_SUMX * cap + i], area);
+  o[5] = (double)table[T_MINY * cap + i];
+  o[6] = (double)table[T_MINX * cap + i];
+  o[7] = (double)(table[T_MAXY * cap + i] + 1);
+  o[8] = (double)(table[T_MAXX * cap + i] + 1);
+  o[9] = (double)(first / W);
+  o[10] = (double)(first % W);
+  o[11] = si;
+  o[12] = __ddiv_rn(si, area);
+}
+
 // out bits = pixels whose label has keep[label] != 0 (per-slice LUT rows of `lut_stride` entries)
 template <typename LabT>
 __global__ void __launch_bounds__(256)
@@ -412,6 +446,13 @@ int pcs_region_table(const void* labels, int label_bytes, const void* intensity,
   }
 #undef LAUNCH
   return pcs_check_launch("region table");
+}
+
+int pcs_table_finalize(const int64_t* table, int64_t cap, const int32_t* offsets, int B, int W, double z0, double* out, void* stream) {
+  PCS_REQUIRE(table && offsets && out && cap >= 1 && B >= 1 && W >= 1, "bad table arguments");
+  PCS_LAUNCH("k_table_finalize", (cudaStream_t)stream, k_table_finalize<<<pcs_blocks(cap, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const long long*)table, cap, offsets, B, W, z0, out));
+  return pcs_check_launch("table finalize");
 }
 
 int pcs_select_labels(const void* labels, int label_bytes, const uint8_t* keep, int64_t lut_stride, uint32_t* out, int B, int H,

@@ -55,31 +55,26 @@ class SegmentResult:
     edt: torch.Tensor  # (Z, H, W) float64
     threshold: torch.Tensor  # (Z,) int32
     counts: torch.Tensor  # (Z,) int32
-    tables: list = field(default_factory=list)  # per chunk: (z0, offsets[B+1], int64 table)
+    tables: list = field(default_factory=list)  # per chunk: (z0, offsets[B+1], int64 table, float64 (cap, 13) table)
     z0: int = 0
+
+    def table_padded(self):
+        """Per chunk ``(offsets[B + 1], float64 (cap, 13) table)`` as left on the device by the pipeline:
+        rows ``[0, offsets[-1])`` are valid.  No host synchronisation."""
+        return [(offsets, ftable) for _, offsets, _, ftable in self.tables]
 
     def table_device(self):
         """Compact ``(n, 13)`` float64 table on the device (one sync to learn the sizes)."""
         parts = []
-        H, W = self.labels.shape[1:]
-        for z0, offsets, table in self.tables:
-            off = offsets.cpu().numpy().astype(np.int64)
-            n = int(off[-1])
+        for _, offsets, table, ftable in self.tables:
+            n = int(offsets[-1])
             if n > table.shape[1]:
                 raise _lib.PcsError(f"region table overflow: {n} regions in a chunk, capacity {table.shape[1]}; raise max_regions_per_slice")
-            if n == 0:
-                continue
-            t = table[:, :n].to(torch.float64)
-            z = torch.repeat_interleave(torch.arange(len(off) - 1, device=table.device, dtype=torch.float64) + float(z0 + self.z0), torch.as_tensor(np.diff(off), device=table.device))
-            lab = torch.arange(n, device=table.device, dtype=torch.float64) - torch.repeat_interleave(torch.as_tensor(off[:-1], device=table.device, dtype=torch.float64), torch.as_tensor(np.diff(off), device=table.device)) + 1.0
-            area = t[ops.T_AREA]
-            first = table[ops.T_FIRST, :n]
-            cols = [z, lab, area, t[ops.T_SUMY] / area, t[ops.T_SUMX] / area, t[ops.T_MINY], t[ops.T_MINX], t[ops.T_MAXY] + 1.0, t[ops.T_MAXX] + 1.0,
-                    torch.div(first, W, rounding_mode="floor").to(torch.float64), (first % W).to(torch.float64), t[ops.T_SUMI], t[ops.T_SUMI] / area]
-            parts.append(torch.stack(cols, dim=1))
+            if n:
+                parts.append(ftable[:n])
         if not parts:
             return torch.zeros((0, len(TABLE_COLUMNS)), dtype=torch.float64, device=self.labels.device)
-        return torch.cat(parts, dim=0)
+        return parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)
 
     def to_numpy(self):
         return {
@@ -138,11 +133,12 @@ class SegmentPlan:
             offsets = torch.empty(B + 1, dtype=torch.int32, device=dev)
             cap = int(max_regions_per_slice) * B
             table = torch.empty((ops.TABLE_COLS, cap), dtype=torch.int64, device=dev)
-            out.tables.append((a, offsets, table))
+            ftable = torch.empty((cap, len(TABLE_COLUMNS)), dtype=torch.float64, device=dev)
+            out.tables.append((a, offsets, table, ftable))
             P = ops._p
             ws = self.ws[i % self.n_streams]
             self.calls.append((P(stack[a:b]), B, H, W, self.dn, self.ms, P(out.mask[a:b]), P(out.labels[a:b]), P(out.refined[a:b]), P(out.edt[a:b]),
-                               P(out.threshold[a:b]), P(out.counts[a:b]), P(offsets), P(table), cap, P(ws), nws))
+                               P(out.threshold[a:b]), P(out.counts[a:b]), P(offsets), P(table), cap, P(ftable), int(z0 + a), P(ws), nws))
         self.graph = None
         if graph:
             self._enqueue()  # warm-up: one-time initialisations must not land in the capture
