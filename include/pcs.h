@@ -144,6 +144,8 @@ int pcs_edt_bits(const uint32_t* bits, int invert, int B, int H, int W, double* 
  *   overlap pixels per label                          tiff_analysis.py:268-279
  * intensity_dtype: -1 none, 0 u8, 1 u16; fg_bits (optional) lets empty words be skipped. */
 int pcs_table_init(int64_t* table, int64_t cap, void* stream);
+/* same, touching only rows [0, offsets[B]) -- for a table whose row count is already on the device */
+int pcs_table_init_rows(int64_t* table, int64_t cap, const int32_t* offsets, int B, void* stream);
 int pcs_region_table(const void* labels, int label_bytes, const void* intensity, int intensity_dtype, const uint32_t* fg_bits,
                      const uint32_t* ov_bits, const int32_t* offsets, int64_t* table, int64_t cap, int B, int H, int W, void* stream);
 /* the float64 table the callers consume, row-major double[cap][13], rows [0, offsets[B]) filled:

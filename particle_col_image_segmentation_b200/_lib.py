@@ -63,6 +63,7 @@ SIGNATURES = {
     "pcs_edt_workspace_bytes": (_Z, [_I, _I, _I]),
     "pcs_edt_bits": (c_int, [_P, _I, _I, _I, _I, _P, _P, _P, _I, _P, _Z, _P]),
     "pcs_table_init": (c_int, [_P, _L, _P]),
+    "pcs_table_init_rows": (c_int, [_P, _L, _P, _I, _P]),
     "pcs_region_table": (c_int, [_P, _I, _P, _I, _P, _P, _P, _P, _L, _I, _I, _I, _P]),
     "pcs_select_labels": (c_int, [_P, _I, _P, _L, _P, _I, _I, _I, _P]),
     "pcs_select_by_area": (c_int, [_P, _P, _P, _L, _P, _L, _P, _I, _I, _I, _P]),

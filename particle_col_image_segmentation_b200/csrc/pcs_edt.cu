@@ -165,24 +165,27 @@ __global__ void k_edt_lut_init() {
 #define EDT_TW 256
 #define EDT_HALO 40
 #define EDT_TWH (EDT_TW + 2 * EDT_HALO)
+#define EDT_ER 16        // rows per CTA: half a band keeps 8 CTAs (2048 threads) resident per SM
 #define EDT_GCLAMP 255u  // vertical distances above EDT_DMAX never win a near search: 8 bits are enough
 __global__ void __launch_bounds__(EDT_TW)
     k_edt_near(const uint32_t* __restrict__ vw, const uint16_t* __restrict__ up, const uint16_t* __restrict__ dn,
                double* __restrict__ dist, int32_t* __restrict__ sq, uint32_t* __restrict__ thr_bits, int thr_sq,
                uint8_t* __restrict__ row_far, int H, int W, int WW, int NB) {
-  __shared__ __align__(16) uint8_t g[32][EDT_TWH];
-  __shared__ __align__(16) uint16_t d2s[32][EDT_TW];
-  __shared__ uint32_t tb[32][EDT_TW / 32];
-  __shared__ unsigned short items[32 * EDT_TW];  // (row << 9 | tile column) of the tile's foreground pixels
+  __shared__ __align__(16) uint8_t g[EDT_ER][EDT_TWH];
+  __shared__ __align__(16) uint16_t d2s[EDT_ER][EDT_TW];
+  __shared__ uint32_t tb[EDT_ER][EDT_TW / 32];
+  __shared__ unsigned short items[EDT_ER * EDT_TW];  // (row << 9 | tile column) of the tile's foreground pixels
   __shared__ int nitems;
   const int tid = threadIdx.x;
   if (tid == 0) nitems = 0;
   const int Wp = WW << 5;
   const int x0 = blockIdx.x * EDT_TW;
-  const int q = blockIdx.y;
+  const int q = blockIdx.y / (32 / EDT_ER);                 // band of 32 rows (one vertical word per column)
+  const int r0 = (blockIdx.y % (32 / EDT_ER)) * EDT_ER;     // first row of the band this CTA owns
   const long long b = blockIdx.z;
   const long long band = (b * NB + q) * (long long)Wp;
-  const int rows = min(32, H - (q << 5));
+  const int rows = min(EDT_ER, H - (q << 5) - r0);
+  if (rows <= 0) return;
   const int cols = min(EDT_TW, W - x0);
   // column words and carries of both column slots of this thread are requested first, so one
   // global round trip is in flight while the tiles are cleared (background: g = 0, distance 0)
@@ -201,9 +204,9 @@ __global__ void __launch_bounds__(EDT_TW)
   }
   {
     uint4* gz = reinterpret_cast<uint4*>(&g[0][0]);
-    for (int i = tid; i < 32 * EDT_TWH / 16; i += EDT_TW) gz[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < EDT_ER * EDT_TWH / 16; i += EDT_TW) gz[i] = make_uint4(0, 0, 0, 0);
     uint4* dz = reinterpret_cast<uint4*>(&d2s[0][0]);
-    for (int i = tid; i < 32 * EDT_TW / 8; i += EDT_TW) dz[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < EDT_ER * EDT_TW / 8; i += EDT_TW) dz[i] = make_uint4(0, 0, 0, 0);
   }
   __syncthreads();
   // pass 1: vertical distances of the foreground pixels; the tile's own foreground pixels are also
@@ -214,24 +217,25 @@ __global__ void __launch_bounds__(EDT_TW)
     if (slot == 1 && tid >= 2 * EDT_HALO) break;
     const int col = tid + slot * EDT_TW;
     const int x = slot ? xb : xa;
-    uint32_t f = slot ? fb : fa;
+    const uint32_t fw = slot ? fb : fa;
+    uint32_t f = (fw >> r0) & ((EDT_ER == 32) ? 0xffffffffu : ((1u << EDT_ER) - 1u));  // this CTA's rows of the column
     if (slot ? inb : ina) {
       if (f) {
-        const uint32_t z = ~f, cu = slot ? cub : cua, cd = slot ? cdb : cda;
+        const uint32_t z = ~fw, cu = slot ? cub : cua, cd = slot ? cdb : cda;
         uint32_t ff = f;
         while (ff) {
           const int r = __ffs(ff) - 1;
           ff &= ff - 1;
-          g[r][col] = (uint8_t)min(edt_vdist(z, r, cu, cd), EDT_GCLAMP);
+          g[r][col] = (uint8_t)min(edt_vdist(z, r0 + r, cu, cd), EDT_GCLAMP);
         }
       }
     } else {
 #pragma unroll 8
-      for (int r = 0; r < 32; ++r) g[r][col] = (uint8_t)EDT_GCLAMP;  // outside the image: no site
+      for (int r = 0; r < EDT_ER; ++r) g[r][col] = (uint8_t)EDT_GCLAMP;  // outside the image: no site
     }
     // work items of interior columns (warp-level exclusive scan of the per-column counts)
     const bool interior = col >= EDT_HALO && col < EDT_HALO + EDT_TW && x < W;
-    if (rows < 32) f &= (1u << rows) - 1u;
+    if (rows < EDT_ER) f &= (1u << rows) - 1u;
     const int cnt = interior ? __popc(f) : 0;
     const unsigned act = __activemask();
     int incl = cnt;
@@ -259,7 +263,7 @@ __global__ void __launch_bounds__(EDT_TW)
   if (thr_bits) {
     // background pixels are at distance 0: start every row word from them (warp w owns word w)
     const int x = x0 + tid;
-    for (int r = 0; r < 32; ++r) {
+    for (int r = 0; r < EDT_ER; ++r) {
       unsigned bg = __ballot_sync(0xffffffffu, x < W && g[r][tid + EDT_HALO] == 0u);
       if ((tid & 31) == 0) tb[r][tid >> 5] = thr_sq >= 0 ? bg : 0u;
     }
@@ -272,7 +276,7 @@ __global__ void __launch_bounds__(EDT_TW)
     const int r = item >> 9, c = item & 511;
     const uint32_t gx = g[r][c];
     if (gx > EDT_DMAX) {
-      row_far[b * H + (q << 5) + r] = 1;  // solved by k_edt_far, which rewrites the whole row
+      row_far[b * H + (q << 5) + r0 + r] = 1;  // solved by k_edt_far, which rewrites the whole row
       continue;
     }
     uint32_t best = gx * gx;
@@ -286,7 +290,7 @@ __global__ void __launch_bounds__(EDT_TW)
   }
   __syncthreads();
   // write the tile: background zeros and foreground distances in one coalesced sweep
-  const long long obase = (b * H + (q << 5)) * (long long)W + x0;
+  const long long obase = (b * H + (q << 5) + r0) * (long long)W + x0;
   if (dist) {
     if (cols == EDT_TW && (W & 1) == 0 && ((((uintptr_t)dist) & 15) == 0)) {
       for (int i = tid; i < rows * (EDT_TW / 2); i += EDT_TW) {
@@ -325,7 +329,7 @@ __global__ void __launch_bounds__(EDT_TW)
     for (int i = tid; i < rows * (EDT_TW / 32); i += EDT_TW) {
       const int r = i / (EDT_TW / 32), w = i % (EDT_TW / 32);
       const int kw = (x0 >> 5) + w;
-      if (kw < WW) thr_bits[(b * H + (q << 5) + r) * (long long)WW + kw] = tb[r][w];
+      if (kw < WW) thr_bits[(b * H + (q << 5) + r0 + r) * (long long)WW + kw] = tb[r][w];
     }
   }
 }
@@ -400,7 +404,7 @@ int pcs_edt_bits(const uint32_t* bits, int invert, int B, int H, int W, double* 
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int WW = pcs_words(W), Wp = WW << 5, NB = (H + 31) / 32;
-  PCS_REQUIRE((long long)NB <= 65535, "too many row bands");
+  PCS_REQUIRE((long long)NB * (32 / EDT_ER) <= 65535, "too many row bands");
   int nwarps = EDT_WARPS;  // far-field solve: one row buffer pair (4 * Wp bytes) per warp in shared memory
   while (nwarps > 1 && (size_t)nwarps * 4 * Wp > 200 * 1024) nwarps >>= 1;
   size_t smem = (size_t)nwarps * 4 * Wp;
@@ -426,7 +430,7 @@ int pcs_edt_bits(const uint32_t* bits, int invert, int B, int H, int W, double* 
       lut_ready[dev] = true;
     }
   }
-  dim3 gn((W + EDT_TW - 1) / EDT_TW, NB, B);
+  dim3 gn((W + EDT_TW - 1) / EDT_TW, NB * (32 / EDT_ER), B);
   PCS_LAUNCH("k_edt_near", st,
              k_edt_near<<<gn, EDT_TW, 0, st>>>(vw, up, dn, dist, sq, thr_bits, thr_sq, row_far, H, W, WW, NB));
   int W2 = 1, L = 0;

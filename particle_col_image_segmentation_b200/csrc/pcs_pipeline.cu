@@ -71,7 +71,7 @@ int pcs_segment_chunk(const uint16_t* img, int B, int H, int W, int denoise_size
     STEP(pcs_unpack_bits(bits, mask, B, H, W, stream));
   }
   STEP(pcs_label_bits(bits, B, H, W, 8, 0, labels, 4, counts, offsets, nullptr, 0, w.ccl, w.ccl_bytes, stream));
-  STEP(pcs_table_init(table, cap, stream));
+  STEP(pcs_table_init_rows(table, cap, offsets, B, stream));
   STEP(pcs_region_table(labels, 4, img, 1, bits, nullptr, offsets, table, cap, B, H, W, stream));
   if (ftable) STEP(pcs_table_finalize(table, cap, offsets, B, W, (double)z0, ftable, stream));
   // small objects out and holes filled in one call: areas come from the table just built, and only

@@ -31,9 +31,9 @@
 #define T_SUMI 8
 #define T_OVERLAP 9
 
-__global__ void k_table_init(long long* __restrict__ table, long long cap) {
+__global__ void k_table_init(long long* __restrict__ table, long long cap, const int* __restrict__ offsets, int B) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= cap) return;
+  if (i >= cap || (offsets && i >= (long long)offsets[B])) return;  // only the rows in use when the count is known
 #pragma unroll
   for (int c = 0; c < PCS_TABLE_COLS; ++c) {
     long long v = 0;
@@ -396,7 +396,13 @@ extern "C" {
 
 int pcs_table_init(int64_t* table, int64_t cap, void* stream) {
   PCS_REQUIRE(cap >= 1 && table != nullptr, "empty table");
-  PCS_LAUNCH("k_table_init", (cudaStream_t)stream, k_table_init<<<pcs_blocks(cap, 256), 256, 0, (cudaStream_t)stream>>>((long long*)table, cap));
+  PCS_LAUNCH("k_table_init", (cudaStream_t)stream, k_table_init<<<pcs_blocks(cap, 256), 256, 0, (cudaStream_t)stream>>>((long long*)table, cap, nullptr, 0));
+  return pcs_check_launch("table init");
+}
+
+int pcs_table_init_rows(int64_t* table, int64_t cap, const int32_t* offsets, int B, void* stream) {
+  PCS_REQUIRE(cap >= 1 && table != nullptr && offsets != nullptr && B >= 1, "empty table");
+  PCS_LAUNCH("k_table_init", (cudaStream_t)stream, k_table_init<<<pcs_blocks(cap, 256), 256, 0, (cudaStream_t)stream>>>((long long*)table, cap, offsets, B));
   return pcs_check_launch("table init");
 }
 
