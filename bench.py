@@ -48,9 +48,38 @@ KERNEL_BYTES_PER_VOXEL = {
     "k_select_by_area": 0.25,
     "k_edt_transpose": 0.25,
     "k_edt_carry": 0.25,
-    "k_edt_near": 8.0 + 0.25,  # the zero background is written by the memset that precedes it (same 8 B/voxel, counted here)
+    "k_edt_near": 8.0 + 0.25,  # every float64 of the tile (background zeros included) is written by this kernel, once
     "k_edt_far": 8.0 + 0.25,
 }
+
+
+# DRAM traffic per voxel of the dominant kernels from the `ncu --set full` capture of profiles/prof_step.py
+# (16 slices of 2048^2 per launch; dram__bytes_read.sum + dram__bytes_write.sum over 67.1 Mvoxel), see
+# profiles/r1e_ncu_full_summary.txt.  Below the algorithmic figure where part of the output is still in L2
+# when the kernel ends.
+NCU_TRAFFIC_BYTES_PER_VOXEL = {
+    "k_edt_near": (16.85 + 477.75) / 67.109,
+    "k_hist_u16": (136.04 + 4.57) / 67.109,
+    "k_ccl_relabel": (60.45 + 209.12) / 67.109,
+}
+
+
+def write_only_probe(dev):
+    """Best-of-5 fill of a 1 GiB buffer: the write-only ceiling of this GPU (the copy figure in
+    MEASURED_PEAKS.json counts read + write bytes; a store-only stream does not reach it)."""
+    import torch
+
+    x = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+    best = 1e9
+    for _ in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        x.fill_(1)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del x
+    return (1 << 30) / (best * 1e-3) / 1e9
 
 
 def parse():
@@ -345,7 +374,10 @@ def run_b200(args):
         bpv = KERNEL_BYTES_PER_VOXEL.get(name, PIPELINE_BYTES_PER_VOXEL)
         avg_ms = kms / kcnt
         achieved = bpv * per_launch_vox / (avg_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        tpv = NCU_TRAFFIC_BYTES_PER_VOXEL.get(name)
+        roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": (tpv * per_launch_vox if tpv else None), "traffic_source": "ncu --set full, profiles/r1e_ncu_full_summary.txt (per voxel, scaled to this launch)" if tpv else None,
+                "write_only_gbs_live": write_only_probe(dev),
                 "bytes_per_voxel": bpv, "avg_launch_ms": avg_ms, "launches": kcnt, "peak_source": peak_src, "kernel_time_share": shares,
                 "kernel_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
                 "timed": "per-kernel CUDA events on the launching stream over a second pass of the same K steps (eager launches)", "ms_per_step_with_events": ms_step_profiled}

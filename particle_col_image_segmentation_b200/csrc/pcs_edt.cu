@@ -65,28 +65,34 @@ __global__ void __launch_bounds__(256)
   vw[(b * NB + q) * (long long)(WW << 5) + (k << 5) + lane] = mine;
 }
 
-// thread per column: distance from the band edge to the nearest background row beyond it
+// thread per (column, direction): distance from the band edge to the nearest background row beyond it.
+// The scan is sequential over the bands of a column, but its loads are independent of the carry, so they
+// are issued sixteen at a time; the upward and the downward scan run in different threads.
 __global__ void __launch_bounds__(128)
     k_edt_carry(const uint32_t* __restrict__ vw, uint16_t* __restrict__ up, uint16_t* __restrict__ dn, int W, int Wp, int NB) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= W) return;
   const long long b = blockIdx.y;
+  const bool down = blockIdx.z != 0;
   const uint32_t* v = vw + b * (long long)NB * Wp + x;
-  uint16_t* u = up + b * (long long)NB * Wp + x;
-  uint16_t* d = dn + b * (long long)NB * Wp + x;
+  uint16_t* o = (down ? dn : up) + b * (long long)NB * Wp + x;
   uint32_t carry = EDT_INF;
-#pragma unroll 4
-  for (int q = 0; q < NB; ++q) {
-    u[(long long)q * Wp] = (uint16_t)carry;  // from row 32q - 1 upwards
-    const uint32_t z = ~__ldg(v + (long long)q * Wp);
-    carry = z ? (uint32_t)__clz(z) : (carry == EDT_INF ? EDT_INF : carry + 32u);  // 31 - msb
-  }
-  carry = EDT_INF;
-#pragma unroll 4
-  for (int q = NB - 1; q >= 0; --q) {
-    d[(long long)q * Wp] = (uint16_t)carry;  // from row 32(q+1) downwards
-    const uint32_t z = ~__ldg(v + (long long)q * Wp);
-    carry = z ? (uint32_t)(__ffs(z) - 1) : (carry == EDT_INF ? EDT_INF : carry + 32u);
+  for (int q0 = 0; q0 < NB; q0 += 16) {
+    uint32_t z[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int q = down ? NB - 1 - (q0 + i) : q0 + i;
+      z[i] = (q0 + i < NB) ? ~__ldg(v + (long long)q * Wp) : 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (q0 + i < NB) {
+        const int q = down ? NB - 1 - (q0 + i) : q0 + i;
+        o[(long long)q * Wp] = (uint16_t)carry;  // up: from row 32q - 1 upwards; down: from row 32(q+1) downwards
+        const uint32_t edge = down ? (uint32_t)(__ffs(z[i]) - 1) : (uint32_t)__clz(z[i]);  // rows between the band edge and its nearest zero
+        carry = z[i] ? edge : (carry == EDT_INF ? EDT_INF : carry + 32u);
+      }
+    }
   }
 }
 
@@ -419,7 +425,7 @@ int pcs_edt_bits(const uint32_t* bits, int invert, int B, int H, int W, double* 
   cudaMemsetAsync(row_far, 0, (size_t)B * H, st);
   PCS_LAUNCH("k_edt_transpose", st,
              k_edt_transpose<<<pcs_blocks((long long)B * NB * WW * 32, 256), 256, 0, st>>>(bits, invert, vw, B, H, W, WW, NB));
-  dim3 gc((W + 127) / 128, B);
+  dim3 gc((W + 127) / 128, B, 2);
   PCS_LAUNCH("k_edt_carry", st, k_edt_carry<<<gc, 128, 0, st>>>(vw, up, dn, W, Wp, NB));
   {
     static bool lut_ready[64] = {};
