@@ -270,8 +270,9 @@ def run_b200(args):
 
     def step(p=None):
         r = (p or plan)()
-        if world > 1:
-            table = pdist.gather_tables(r.table_device())  # the one exchange step: row counts, then rows
+        if world > 1:  # the one exchange step: row counts (one host sync), then rows
+            pads = r.table_padded()
+            table = pdist.gather_tables_padded(pads[0][1], pads[0][0]) if len(pads) == 1 else pdist.gather_tables(r.table_device())
         else:
             table = r.table_padded()  # finished float64 table in HBM (row count in offsets[-1]); no host sync
         return r, table

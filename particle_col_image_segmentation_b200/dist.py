@@ -41,6 +41,24 @@ def gather_tables(local_table, group=None):
     return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
 
 
+def gather_tables_padded(ftable, offsets, group=None):
+    """The same gather for a table still in its padded device form (``SegmentResult.table_padded()``:
+    ``(cap, C)`` rows of which the first ``offsets[-1]`` are valid).  Row counts are exchanged first and
+    read back in ONE host synchronisation; every rank then contributes its first ``max(counts)`` rows."""
+    n_local = offsets[-1:].to(torch.int64)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return ftable[: int(n_local.item())]
+    world = dist.get_world_size(group)
+    counts = torch.empty(world, dtype=torch.int64, device=ftable.device)
+    dist.all_gather_into_tensor(counts, n_local, group=group)
+    counts = counts.cpu().tolist()
+    cap = min(max(max(counts), 1), ftable.shape[0])
+    flat = torch.empty((world * cap, ftable.shape[1]), dtype=ftable.dtype, device=ftable.device)
+    dist.all_gather_into_tensor(flat, ftable[:cap].contiguous(), group=group)
+    parts = flat.view(world, cap, ftable.shape[1])
+    return torch.cat([parts[r, :c] for r, c in enumerate(counts)], dim=0)
+
+
 def segment_zstack_sharded(stack_local, z0, group=None, **kwargs):
     """Run the pipeline on this rank's slices (global index of the first one: ``z0``) and
     gather the region tables.  Returns ``(SegmentResult for the local slices, global table)``."""

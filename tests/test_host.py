@@ -91,6 +91,13 @@ z0, z1 = pdist.shard_range(10, rank, world)
 local = torch.from_numpy(full[(full[:, 0] >= z0) & (full[:, 0] < z1)])
 out = pdist.gather_tables(local)
 assert out.shape == full.shape and np.array_equal(out.numpy(), full), (rank, out.shape)
+# the padded form the device pipeline leaves behind: (cap, 13) rows + offsets whose last entry is the row count
+cap = 64
+padded = torch.full((cap, 13), -7.0, dtype=torch.float64)
+padded[: local.shape[0]] = local
+offsets = torch.tensor([0, local.shape[0]], dtype=torch.int32)
+out2 = pdist.gather_tables_padded(padded, offsets)
+assert out2.shape == full.shape and np.array_equal(out2.numpy(), full), (rank, out2.shape)
 empty = pdist.gather_tables(torch.zeros((0, 13), dtype=torch.float64) if rank == 1 else local)
 assert empty.shape[0] == local.shape[0] * (1 if rank == 0 else 0) + (0 if rank == 1 else 0) or True
 dist.barrier()
