@@ -40,6 +40,71 @@ def split_channels(zstack, channel_indices=(1, 2)):
     return {cmap[c]: zstack[:, c] for c in channel_indices}
 
 
+def get_clean_file_name(input_file):
+    """``(channel suffix, name without it)`` as split_zstack.py:21-32 derives them: the stem up to the
+    first dot, minus the channel list and the ``_zstack`` / ``_mip`` markers."""
+    stem = input_file.split(".")[0]
+    for marker in ("CY5_RFP_GFP_DAPI", "RFP_GFP"):
+        if marker + "_" in stem:
+            suffix = "_" + marker
+            return suffix, stem.replace(suffix, "").replace("_zstack", "").replace("_mip", "")
+    return "", stem
+
+
+def channel_folder_name(destination, used_channels, channel_name):
+    """Folder a channel's planes go to (split_zstack.py:34-38, without creating it)."""
+    return destination.replace(".tif", "").replace("_mip", "").replace(used_channels, "") + "_" + channel_name
+
+
+def process_tif(input_file, channel_indices=(1, 2), move=True):
+    """split_zstack.py:40-65 with this repo's TIFF reader / writer: the stack file is moved into a folder
+    named after it, read as ``(Z, C, Y, X)`` and every selected ``z_slice[channel]`` plane is written to
+    ``<folder>_<channel>/<name>_z<i>_<channel>.tif``.  Returns the list of files written.
+    ``move=False`` leaves the input where it is (the planes still go next to the would-be destination)."""
+    import os
+
+    from . import tiff_io
+
+    stem_end = input_file.split("/")[-1].split(".")[0]
+    used_channels, clean = get_clean_file_name(input_file)
+    os.makedirs(clean, exist_ok=True)
+    destination = os.path.join(clean, os.path.basename(input_file))
+    if move:
+        os.rename(input_file, destination)
+    if not input_file.endswith(".tif"):
+        return []
+    zstack = tiff_io.read_stack(destination if move else input_file)
+    if zstack.ndim != 4:
+        raise ValueError(f"expected a (Z, C, Y, X) stack in {input_file}, got shape {zstack.shape}")
+    planes = split_channels(zstack, tuple(channel_indices))
+    written = []
+    for name, stack in planes.items():
+        folder = channel_folder_name(destination, used_channels, name)
+        os.makedirs(folder, exist_ok=True)
+        for z in range(stack.shape[0]):
+            out = os.path.join(folder, plane_name(stem_end.replace(used_channels, ""), z, name))
+            tiff_io.write_plane(out, stack[z])
+            written.append(out)
+    return written
+
+
+def segment_tif(path, channel=1, **kwargs):
+    """Read a ``(Z, C, Y, X)`` (or ``(Z, Y, X)``) uint16 stack file into pinned memory and run the segment
+    pipeline on one channel; returns the dict of pinned host tensors of ``segment_zstack_pinned``."""
+    from . import tiff_io
+
+    t = tiff_io.read_stack_pinned(path)
+    if t.dim() == 4:
+        t = t[:, channel].contiguous()
+        if torch.cuda.is_available():
+            t = t.pin_memory()
+    if t.dim() != 3 or t.dtype != torch.uint16:
+        raise _lib.PcsError(f"segment_tif expects a uint16 (Z, [C,] Y, X) stack, got {tuple(t.shape)} {t.dtype}")
+    out = alloc_host_outputs(*t.shape)
+    segment_zstack_pinned(t, out, **kwargs)
+    return out
+
+
 def plane_name(base, z, channel):
     """File name the reference would give the plane (split_zstack.py:63)."""
     return f"{base}_z{z}_{channel}.tif"
