@@ -160,6 +160,10 @@ int pcs_select_by_area(const int32_t* labels, const uint32_t* fg_bits, const int
                        int64_t min_size, uint32_t* out, int B, int H, int W, void* stream);
 /* sum(sum(plane .* roimask)) for K float64 planes (.m:122-132, :186-196); out float64[n_rois][K] */
 int pcs_roi_sums_f64(const int32_t* labels, const double* planes, int K, int64_t npix, int n_rois, double* out, void* stream);
+/* nearest neighbour of every a_i among the b_j (float64 pairs): distance and (optional) index, first minimum
+ * on ties; exclude_self skips j == i (nearest OTHER cell of one strain).  No b point -> inf, index -1.
+ * Cell-cell distances within and across strains: refine_boundaries.py:8-12 (goal 3), model .m:260-263. */
+int pcs_nearest_f64(const double* a, int64_t na, const double* b, int64_t nb, int exclude_self, double* out_dist, int64_t* out_index, void* stream);
 /* out[i] = min_j |a_i - b_j| for (x, y) float64 pairs (pdist2 + min, .m:260-263, :301-304) */
 int pcs_min_dist_f64(const double* a, int64_t na, const double* b, int64_t nb, double* out, void* stream);
 

@@ -254,3 +254,29 @@ def summarize_positions(result):
             for m in recs
         ]
     return out
+
+
+def get_cell_cell_distances(cell_pos):
+    """Brute-force statement of the nearest-neighbour distances (refine_boundaries.py:8-12 goal 3; model
+    .m:260-263 ``pdist2`` + ``min``): ``{(a, b): (distance, index)}`` per cell of strain ``a``; within a strain
+    the cell itself is excluded.  Same operation order as the device kernel: (dx*dx + dy*dy), sqrt last."""
+    pts = {k: np.array([r.centroid for r in v], dtype=np.float64).reshape(-1, 2) for k, v in cell_pos.items()}
+    out = {}
+    for a, pa in pts.items():
+        for b, pb in pts.items():
+            if len(pa) == 0:
+                out[(a, b)] = (np.zeros(0), np.zeros(0, dtype=np.int64))
+                continue
+            if len(pb) == 0:
+                out[(a, b)] = (np.full(len(pa), np.inf), np.full(len(pa), -1, dtype=np.int64))
+                continue
+            dx = pa[:, None, 0] - pb[None, :, 0]
+            dy = pa[:, None, 1] - pb[None, :, 1]
+            d2 = dx * dx + dy * dy
+            if a == b:
+                np.fill_diagonal(d2, np.inf)
+            j = np.argmin(d2, axis=1)
+            d = np.sqrt(d2[np.arange(len(pa)), j])
+            j = np.where(np.isinf(d), -1, j)
+            out[(a, b)] = (d, j.astype(np.int64))
+    return out

@@ -392,6 +392,42 @@ __global__ void __launch_bounds__(128)
   out[i] = sqrt(best);
 }
 
+// nearest neighbour of every a_i among the b_j (optionally skipping j == i: nearest OTHER cell of the same
+// strain, refine_boundaries.py:8-12 goal 3; the MATLAB model is pdist2 + min, .m:260-263).  b is staged
+// through shared memory 128 points at a time; squared distances in numpy order without FMA, first minimum
+// wins (np.argmin), one IEEE sqrt at the end.
+__global__ void __launch_bounds__(128)
+    k_nearest(const double* __restrict__ a, long long na, const double* __restrict__ b, long long nb, int exclude_self,
+              double* __restrict__ out_d, long long* __restrict__ out_j) {
+  __shared__ double sb[128][2];
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const double ax = i < na ? a[2 * i] : 0.0, ay = i < na ? a[2 * i + 1] : 0.0;
+  double best = __longlong_as_double(0x7ff0000000000000LL);
+  long long at = -1;
+  for (long long j0 = 0; j0 < nb; j0 += 128) {
+    const long long j = j0 + threadIdx.x;
+    __syncthreads();
+    if (j < nb) {
+      sb[threadIdx.x][0] = b[2 * j];
+      sb[threadIdx.x][1] = b[2 * j + 1];
+    }
+    __syncthreads();
+    const int n = (int)min(128LL, nb - j0);
+    for (int t = 0; t < n; ++t) {
+      const double dx = __dsub_rn(ax, sb[t][0]), dy = __dsub_rn(ay, sb[t][1]);
+      const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+      if (d2 < best && !(exclude_self && j0 + t == i)) {
+        best = d2;
+        at = j0 + t;
+      }
+    }
+  }
+  if (i < na) {
+    out_d[i] = sqrt(best);
+    if (out_j) out_j[i] = at;
+  }
+}
+
 extern "C" {
 
 int pcs_table_init(int64_t* table, int64_t cap, void* stream) {
@@ -491,6 +527,15 @@ int pcs_roi_sums_f64(const int32_t* labels, const double* planes, int K, int64_t
   cudaMemsetAsync(out, 0, (size_t)n_rois * K * 8, st);
   PCS_LAUNCH("k_roi_sums", st, k_roi_sums<<<pcs_blocks(npix, 256), 256, 0, st>>>(labels, planes, K, npix, n_rois, out));
   return pcs_check_launch("roi sums");
+}
+
+int pcs_nearest_f64(const double* a, int64_t na, const double* b, int64_t nb, int exclude_self, double* out_dist, int64_t* out_index,
+                    void* stream) {
+  if (na <= 0) return PCS_OK;
+  PCS_REQUIRE(a && out_dist && (b || nb == 0) && nb >= 0, "null argument");
+  PCS_LAUNCH("k_nearest", (cudaStream_t)stream, k_nearest<<<pcs_blocks(na, 128), 128, 0, (cudaStream_t)stream>>>(
+      a, na, b, nb, exclude_self, out_dist, (long long*)out_index));
+  return pcs_check_launch("nearest");
 }
 
 int pcs_min_dist_f64(const double* a, int64_t na, const double* b, int64_t nb, double* out, void* stream) {

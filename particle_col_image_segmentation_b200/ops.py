@@ -380,3 +380,14 @@ def min_dist(a_xy, b_xy):
     out = torch.empty(int(a_xy.shape[0]), dtype=torch.float64, device=a_xy.device)
     _lib.call("pcs_min_dist_f64", _p(a_xy), int(a_xy.shape[0]), _p(b_xy), int(b_xy.shape[0]), _p(out), _stream())
     return out
+
+
+def nearest(a_xy, b_xy, exclude_self=False):
+    """Distance to and index of the nearest ``b`` point for every ``a`` point (``(n, 2)`` float64 CUDA
+    tensors); ``exclude_self`` skips ``j == i`` (use with ``b_xy is a_xy``)."""
+    a_xy, b_xy = a_xy.contiguous(), b_xy.contiguous()
+    na = int(a_xy.shape[0])
+    d = torch.empty(na, dtype=torch.float64, device=a_xy.device)
+    j = torch.empty(na, dtype=torch.int64, device=a_xy.device)
+    _lib.call("pcs_nearest_f64", _p(a_xy), na, _p(b_xy), int(b_xy.shape[0]), int(bool(exclude_self)), _p(d), _p(j), _stream())
+    return d, j

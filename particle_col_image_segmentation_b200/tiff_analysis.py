@@ -303,6 +303,31 @@ def combine_channels(rfp_base, channel_ds_arrs, cell_strains):
     return rfp_base
 
 
+def get_cell_cell_distances(cell_pos):
+    """Nearest-neighbour distances between cells, within and across strains -- goal 3 of the author's notes
+    (refine_boundaries.py:8-12: "the distance between each cell of a given strain and its nearest neighbor of
+    the same strain, and ... of a different strain"), not yet written in the reference; the MATLAB script's
+    ``pdist2`` + ``min`` block (.m:260-263) is the model.  ``cell_pos`` is the dict of region lists that
+    ``get_cell_positions_and_areas`` returns.  Result: ``{(strain_a, strain_b): (distances, indices)}`` with one
+    entry per cell of ``strain_a`` (centroid to centroid, pixels; ``inf`` / ``-1`` when ``strain_b`` has no
+    other cell), indices into ``cell_pos[strain_b]``."""
+    import torch
+
+    from . import _io, ops
+
+    dev = _io.device()
+    pts = {k: torch.as_tensor(np.array([r.centroid for r in v], dtype=np.float64).reshape(-1, 2), device=dev) for k, v in cell_pos.items()}
+    out = {}
+    for a, pa in pts.items():
+        for b, pb in pts.items():
+            if pa.shape[0] == 0:
+                out[(a, b)] = (np.zeros(0), np.zeros(0, dtype=np.int64))
+                continue
+            d, j = ops.nearest(pa, pb, exclude_self=(a == b))
+            out[(a, b)] = (d.cpu().numpy(), j.cpu().numpy())
+    return out
+
+
 def get_cell_counts_and_densities(cell_pos, cell_clusters, particle_area):
     """tiff_analysis.py:1018-1038 -- host arithmetic over the region lists."""
     cell_count, cell_density, cell_area_ratio = {}, {}, {}

@@ -137,3 +137,31 @@ def test_nanosims(ta, k):
     c, t, m = nanosims.activity_vs_distance(got[:, 2 + k], got[:, -1], np.linspace(0, 5, 11))
     c2, t2, m2 = onano.activity_vs_distance(want[:, 2 + k], want[:, -1], np.linspace(0, 5, 11))
     assert np.array_equal(c, c2) and np.array_equal(t, t2)
+
+
+def test_cell_cell_distances_match_brute_force(ta):
+    """SURVEY 8f row 4 (refine_boundaries.py:8-12 goal 3): nearest same-strain / other-strain neighbour."""
+    img = synth.multi_class_image(384, 384, seed=21)
+    cell_pos, _, _, _ = ta.get_cell_positions_and_areas(img, ta.BASE_TYPE_MAP)
+    cell_pos = dict(cell_pos)
+    cell_pos["ghost"] = []  # a strain without cells
+    got = ta.get_cell_cell_distances(cell_pos)
+    want = ol2.get_cell_cell_distances(cell_pos)
+    assert set(got) == set(want) and any(len(v[0]) > 3 for v in got.values())
+    for k in want:
+        assert np.array_equal(got[k][0], want[k][0]), k  # bit-exact distances
+        assert np.array_equal(got[k][1], want[k][1]), k
+    # a strain with a single cell has no same-strain neighbour
+    from particle_col_image_segmentation_b200 import ops
+
+    one = torch.tensor([[3.0, 4.0]], dtype=torch.float64, device="cuda")
+    d, j = ops.nearest(one, one, exclude_self=True)
+    assert np.isinf(d.item()) and j.item() == -1
+    pts = torch.rand((1000, 2), dtype=torch.float64, device="cuda") * 500
+    d, j = ops.nearest(pts, pts, exclude_self=True)
+    p = pts.cpu().numpy()
+    dx = p[:, None, 0] - p[None, :, 0]
+    dy = p[:, None, 1] - p[None, :, 1]
+    d2 = dx * dx + dy * dy
+    np.fill_diagonal(d2, np.inf)
+    assert np.array_equal(j.cpu().numpy(), d2.argmin(1)) and np.array_equal(d.cpu().numpy(), np.sqrt(d2.min(1)))
