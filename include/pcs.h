@@ -167,6 +167,16 @@ int pcs_nearest_f64(const double* a, int64_t na, const double* b, int64_t nb, in
 /* out[i] = min_j |a_i - b_j| for (x, y) float64 pairs (pdist2 + min, .m:260-263, :301-304) */
 int pcs_min_dist_f64(const double* a, int64_t na, const double* b, int64_t nb, double* out, void* stream);
 
+/* ---- NanoSIMS ratio images (.m:17-69) --------------------------------------------------------
+ * imgaussfilt(A, sigma): taps 2*ceil(2*sigma)+1, replicate border, columns then rows, float64; tmp is
+ * scratch of the same size as the images */
+int pcs_gauss_f64(const double* in, double* out, double* tmp, double sigma, int B, int H, int W, void* stream);
+/* ratio = num ./ ((d0 + d1) + d2) (null denominators are skipped; all null: ratio = num);
+ * *maxv = max over the non-NaN ratios (.m:45 `max(N15gauss(:)./(N15gauss(:)+N14gauss(:)))`) */
+int pcs_ratio_f64(const double* num, const double* d0, const double* d1, const double* d2, double* ratio, double* maxv, int64_t n, void* stream);
+/* uint8(x .* (255 / *maxv)) with MATLAB's conversion: round half away from zero, saturate, NaN -> 0 (.m:31-37) */
+int pcs_scale_u8_f64(const double* x, const double* maxv, uint8_t* out, int64_t n, void* stream);
+
 /* ---- the whole segment pipeline for one chunk of slices -----------------------------------
  * threshold (Otsu) -> size x size binary median -> label (8-connected) -> per-label table ->
  * small objects (< min_size) out, holes filled -> exact EDT.  Stands in for the chain

@@ -119,3 +119,74 @@ def activity_vs_distance(activity, distance, edges):
     tot = np.bincount(idx, weights=activity, minlength=nb)
     with np.errstate(divide="ignore", invalid="ignore"):
         return cnt, tot, tot / cnt
+
+
+# ---------------------------------------------------------------- ratio images (.m:17-69)
+def imgaussfilt(a, sigma):
+    """``imgaussfilt(A, sigma)`` (.m:43): replicate border, columns then rows, products summed in tap order
+    (one rounding per operation, as the device kernel does).  MATLAB's own summation order is not documented."""
+    a = np.asarray(a, dtype=np.float64)
+    r = int(np.ceil(2.0 * sigma))
+    import math
+
+    w = [math.exp(-float(t * t) / (2.0 * sigma * sigma)) for t in range(-r, r + 1)]  # libm exp, as the C side
+    s = 0.0
+    for v in w:
+        s += v
+    w = [v / s for v in w]
+    h, wd = a.shape
+    pad = np.pad(a, ((r, r), (0, 0)), mode="edge")
+    tmp = np.zeros_like(a)
+    for t in range(2 * r + 1):
+        tmp = tmp + w[t] * pad[t : t + h]
+    pad = np.pad(tmp, ((0, 0), (r, r)), mode="edge")
+    out = np.zeros_like(a)
+    for t in range(2 * r + 1):
+        out = out + w[t] * pad[:, t : t + wd]
+    return out
+
+
+def scaled_uint8(num, dens=()):
+    """``uint8(R .* (255 / max(R(:))))``, MATLAB conversion: round half away from zero, saturate, NaN -> 0."""
+    r = np.asarray(num, dtype=np.float64)
+    if dens:
+        den = np.asarray(dens[0], dtype=np.float64)
+        for d in dens[1:]:
+            den = den + np.asarray(d, dtype=np.float64)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            r = r / den
+    with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
+        v = r * (255.0 / np.nanmax(r))
+        fl = np.floor(np.abs(v))
+        q = np.sign(v) * (fl + (np.abs(v) - fl >= 0.5))  # round half away from zero, exactly
+    q = np.where(np.isnan(q), 0.0, np.clip(q, 0.0, 255.0))
+    return q.astype(np.uint8)
+
+
+def ratio_images(ions):
+    """.m:17-69 with the script's variable names (see the device mirror for the line map)."""
+    raw = {k: np.asarray(v, dtype=np.float64)[1:-1, 1:-1] for k, v in ions.items()}
+    g1 = {k: imgaussfilt(raw[k], 1) for k in ("15N12C", "14N12C", "16O", "17O", "18O") if k in raw}
+    g15 = {k: imgaussfilt(raw[k], 1.5) for k in ("12C", "13C", "Esi") if k in raw}
+    out = {}
+    for k, name in (("12C", "C12img"), ("13C", "C13img"), ("14N12C", "N14C12img"), ("15N12C", "N15C12img"), ("16O", "O16img"), ("17O", "O17img"), ("18O", "O18img")):
+        if k in raw:
+            out[name] = scaled_uint8(raw[k])
+    if "15N12C" in raw and "14N12C" in raw:
+        out["N15ratioimg"] = scaled_uint8(g1["15N12C"], (g1["15N12C"], g1["14N12C"]))
+        out["N15ratimg"] = scaled_uint8(raw["15N12C"], (raw["15N12C"], raw["14N12C"]))
+    if "12C" in raw and "13C" in raw:
+        out["C13ratioimg"] = scaled_uint8(g15["13C"], (g15["13C"], g15["12C"]))
+        out["C13ratimg"] = scaled_uint8(raw["13C"], (raw["13C"], raw["12C"]))
+        if "14N12C" in raw:
+            out["N14C12C12ratio"] = scaled_uint8(g1["14N12C"], (g15["12C"],))
+    if all(k in raw for k in ("16O", "17O", "18O")):
+        dens_g = (g1["18O"], g1["17O"], g1["16O"])
+        dens_r = (raw["18O"], raw["17O"], raw["16O"])
+        out["O17ratioimg"] = scaled_uint8(g1["17O"], dens_g)
+        out["O18ratioimg"] = scaled_uint8(g1["18O"], dens_g)
+        out["O17ratimg"] = scaled_uint8(raw["17O"], dens_r)
+        out["O18ratimg"] = scaled_uint8(raw["18O"], dens_r)
+    if "Esi" in raw and "14N12C" in raw:
+        out["N14C12ESIratio"] = scaled_uint8(raw["14N12C"], (raw["Esi"],))
+    return out

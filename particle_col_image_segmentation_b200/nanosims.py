@@ -92,3 +92,74 @@ def activity_vs_distance(activity, distance, edges):
     tot = np.bincount(idx, weights=activity, minlength=nb)
     with np.errstate(divide="ignore", invalid="ignore"):
         return cnt, tot, tot / cnt
+
+
+# ---------------------------------------------------------------- ratio images (.m:17-69)
+def _f64_image(a):
+    t = _io.to_device(a, torch.float64)
+    if t.dim() != 2:
+        raise ValueError(f"expected a 2-D plane, got shape {tuple(t.shape)}")
+    return t
+
+
+def imgaussfilt(a, sigma):
+    """MATLAB ``imgaussfilt(A, sigma)`` with its defaults (.m:43): kernel ``2*ceil(2*sigma)+1``, replicate
+    border, double precision.  numpy in -> numpy out, CUDA tensor in -> CUDA tensor out."""
+    t = _f64_image(a)
+    out, tmp = torch.empty_like(t), torch.empty_like(t)
+    H, W = t.shape
+    _lib_call("pcs_gauss_f64", ops._p(t), ops._p(out), ops._p(tmp), float(sigma), 1, int(H), int(W), ops._stream())
+    return _io.back(out, _io.is_numpy(a))
+
+
+def _lib_call(name, *args):
+    from . import _lib
+
+    _lib.call(name, *args)
+
+
+def scaled_uint8(num, dens=()):
+    """``uint8(R .* (255 / max(R(:))))`` with ``R = num ./ (dens[0] + dens[1] + ...)`` (``R = num`` without
+    denominators): the conversion behind every ``...img`` variable of the script (.m:31-37, :45-69)."""
+    n = _f64_image(num)
+    ds = [_f64_image(d) for d in dens]
+    if len(ds) > 3:
+        raise ValueError("at most three denominators")
+    ratio = torch.empty_like(n)
+    maxv = torch.empty(1, dtype=torch.float64, device=n.device)
+    p = [ops._p(d) for d in ds] + [0] * (3 - len(ds))
+    _lib_call("pcs_ratio_f64", ops._p(n), p[0], p[1], p[2], ops._p(ratio), ops._p(maxv), int(n.numel()), ops._stream())
+    out = torch.empty(n.shape, dtype=torch.uint8, device=n.device)
+    _lib_call("pcs_scale_u8_f64", ops._p(ratio), ops._p(maxv), ops._p(out), int(n.numel()), ops._stream())
+    return _io.back(out, _io.is_numpy(num))
+
+
+def ratio_images(ions):
+    """The image block at the top of the script (.m:17-69).  ``ions`` maps the seven plane names of
+    ``PLANES_7`` (and optionally ``"Esi"``) to the raw square ``IM`` arrays; returns the uint8 images under the
+    script's own variable names.  The one-pixel frame is cropped first (``IM(2:n-1, 2:n-1)``, .m:18-28)."""
+    raw = {k: _f64_image(np.asarray(v, dtype=np.float64)[1:-1, 1:-1]) for k, v in ions.items()}
+    g1 = {k: imgaussfilt(raw[k], 1) for k in ("15N12C", "14N12C", "16O", "17O", "18O") if k in raw}
+    g15 = {k: imgaussfilt(raw[k], 1.5) for k in ("12C", "13C", "Esi") if k in raw}
+    out = {}
+    for k, name in (("12C", "C12img"), ("13C", "C13img"), ("14N12C", "N14C12img"), ("15N12C", "N15C12img"), ("16O", "O16img"), ("17O", "O17img"), ("18O", "O18img")):
+        if k in raw:
+            out[name] = scaled_uint8(raw[k])
+    if "15N12C" in raw and "14N12C" in raw:
+        out["N15ratioimg"] = scaled_uint8(g1["15N12C"], (g1["15N12C"], g1["14N12C"]))  # .m:45
+        out["N15ratimg"] = scaled_uint8(raw["15N12C"], (raw["15N12C"], raw["14N12C"]))  # .m:65
+    if "12C" in raw and "13C" in raw:
+        out["C13ratioimg"] = scaled_uint8(g15["13C"], (g15["13C"], g15["12C"]))  # .m:54
+        out["C13ratimg"] = scaled_uint8(raw["13C"], (raw["13C"], raw["12C"]))  # .m:66
+        if "14N12C" in raw:
+            out["N14C12C12ratio"] = scaled_uint8(g1["14N12C"], (g15["12C"],))  # .m:53
+    if all(k in raw for k in ("16O", "17O", "18O")):
+        dens_g = (g1["18O"], g1["17O"], g1["16O"])
+        dens_r = (raw["18O"], raw["17O"], raw["16O"])
+        out["O17ratioimg"] = scaled_uint8(g1["17O"], dens_g)  # .m:59
+        out["O18ratioimg"] = scaled_uint8(g1["18O"], dens_g)  # .m:60
+        out["O17ratimg"] = scaled_uint8(raw["17O"], dens_r)  # .m:67
+        out["O18ratimg"] = scaled_uint8(raw["18O"], dens_r)  # .m:68
+    if "Esi" in raw and "14N12C" in raw:
+        out["N14C12ESIratio"] = scaled_uint8(raw["14N12C"], (raw["Esi"],))  # .m:64 overwrites .m:63
+    return {k: v.cpu().numpy() for k, v in out.items()}

@@ -165,3 +165,42 @@ def test_cell_cell_distances_match_brute_force(ta):
     d2 = dx * dx + dy * dy
     np.fill_diagonal(d2, np.inf)
     assert np.array_equal(j.cpu().numpy(), d2.argmin(1)) and np.array_equal(d.cpu().numpy(), np.sqrt(d2.min(1)))
+
+
+def test_nanosims_ratio_images():
+    """SURVEY 8f row 3 (.m:17-69): imgaussfilt + isotope ratio + uint8 scaling.  The device kernels and
+    oracle/nanosims.py do the same IEEE operations in the same order: bit-exact.  Against an independent
+    Gaussian (scipy correlate1d, mode='nearest') the filter agrees to 1e-13 relative (different summation
+    order); MATLAB itself cannot be run here (parity with MATLAB unpinned, north_star tolerance 1e-5)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from particle_col_image_segmentation_b200 import nanosims
+
+    planes, _, _, _ = synth.nanosims_stack(n=130, k=7, n_rois=30, seed=8)
+    rng = np.random.default_rng(2)
+    ions = {name: planes[i] for i, name in enumerate(onano.PLANES_7)}
+    ions["Esi"] = rng.poisson(40, planes[0].shape).astype(np.float64)
+    ions["12C"][5, 7] = 0.0
+    ions["13C"][5, 7] = 0.0  # 0 / 0 -> NaN in the raw ratio image, uint8(NaN) = 0
+    for sigma in (1, 1.5, 0.6, 3.2):
+        got = nanosims.imgaussfilt(ions["17O"], sigma)
+        want = onano.imgaussfilt(ions["17O"], sigma)
+        assert got.dtype == np.float64 and np.array_equal(got, want), sigma
+        r = int(np.ceil(2 * sigma))
+        x = np.arange(-r, r + 1.0)
+        w = np.exp(-x * x / (2 * sigma * sigma))
+        w /= w.sum()
+        ref = ndi.correlate1d(ndi.correlate1d(ions["17O"], w, axis=0, mode="nearest"), w, axis=1, mode="nearest")
+        np.testing.assert_allclose(got, ref, rtol=1e-13, atol=0)
+    got = nanosims.ratio_images(ions)
+    want = onano.ratio_images(ions)
+    assert set(got) == set(want) and len(got) == 17
+    for k in want:
+        assert got[k].dtype == np.uint8 and got[k].shape == (128, 128)
+        assert np.array_equal(got[k], want[k]), (k, np.argwhere(got[k] != want[k])[:4])
+        assert got[k].max() == 255 or k == "N14C12ESIratio"
+    assert got["C13ratimg"][4, 6] == 0  # the 0/0 pixel (after the one-pixel crop)
+    # rounding is half away from zero and saturating
+    x = np.array([[0.0, 0.5, 1.5, 2.5, 254.5, 255.0, 127.49999999999999]])
+    assert nanosims.scaled_uint8(x).tolist() == [[0, 1, 2, 3, 255, 255, 127]]
+    assert np.array_equal(nanosims.scaled_uint8(x), onano.scaled_uint8(x))
