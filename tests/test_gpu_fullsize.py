@@ -59,6 +59,34 @@ def test_config2_zstack_2048x2048x64(mods):
     assert torch.equal(table, res2.table_device())
 
 
+def test_config5_shard_2048x2048x256(mods):
+    """configs[4] / north_star target: one 2048x2048x256 uint16 stack (a GPU's share of the 64-stack batch),
+    processed in chunks of 64 slices.  Size-independent properties on the whole result, the oracle on two
+    slices, and the sharding identity: slices [128, 192) run as a separate shard give the same bytes."""
+    Z, S = 256, 2048
+    stack = synth.zstack_u16_device(Z, S, S, seed=1005, device=torch.device("cuda"))
+    res = mods.seg.SegmentPlan(stack, chunk=64, graph=True)()
+    table = res.table_device()
+    torch.cuda.synchronize()
+    assert int(table.shape[0]) == int(res.counts.sum())
+    assert torch.equal(res.labels.amax(dim=(1, 2)).cpu(), res.counts.cpu())
+    assert torch.equal((res.labels != 0), res.mask.bool())
+    assert bool(((res.edt > 0) == res.refined.bool()).all())
+    assert float(table[:, 2].sum()) == float(res.mask.sum())
+    assert bool((table[1:, 0] >= table[:-1, 0]).all())  # rows ordered by slice, then by label
+    for zi in (5, 250):
+        want = opipe.segment_slice(stack[zi].cpu().numpy(), z=zi)
+        assert np.array_equal(res.labels[zi].cpu().numpy(), want["labels"])
+        assert np.array_equal(res.edt[zi].cpu().numpy(), want["edt"])
+        assert np.array_equal(table[table[:, 0] == zi].cpu().numpy(), want["table"])
+    shard = mods.seg.SegmentPlan(stack[128:192], chunk=16, z0=128)()
+    st = shard.table_device()
+    torch.cuda.synchronize()
+    for k in ("mask", "labels", "refined", "edt", "threshold", "counts"):
+        assert torch.equal(getattr(shard, k), getattr(res, k)[128:192]), k
+    assert torch.equal(st, table[(table[:, 0] >= 128) & (table[:, 0] < 192)])
+
+
 def test_config3_touching_particles_4096(mods):
     """configs[2]: refine_boundaries morphology + EDT on 4096x4096 masks with ~10k touching particles."""
     mask, prob = synth.touching_particles(4096, 4096, seed=1003)
