@@ -90,14 +90,15 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--slices", type=int, default=64, help="slices per GPU (configs[1]: 64; north_star target: 256)")
     ap.add_argument("--size", type=int, default=2048)
-    ap.add_argument("--chunk", type=int, default=64, help="slices per batched launch")
+    ap.add_argument("--chunk", type=int, default=32, help="slices per batched launch")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-chunk", type=int, default=4, help="slices per pipeline stage of the host-buffer path (H2D / kernels / D2H overlap chunk-wise)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="slices in the CPU baseline sample (0 = one per host core, at most 32)")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--streams", type=int, default=1, help="streams the chunks of a step are spread over")
+    ap.add_argument("--streams", type=int, default=2, help="streams the chunks of a step are spread over (inside the captured graph)")
+    ap.add_argument("--no-gather", action="store_true", help="diagnosis: skip the table gather of an N > 1 step")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a captured CUDA graph")
     return ap.parse_args()
 
@@ -268,11 +269,15 @@ def run_b200(args):
     res = plan_eager.out
     plan = split_zstack.SegmentPlan(stack, chunk=args.chunk, z0=rank * Z, out=None, graph=True, streams=args.streams) if not args.no_graph else plan_eager
 
+    gatherers = []
+
     def step(p=None):
         r = (p or plan)()
-        if world > 1:  # the one exchange step: row counts (one host sync), then rows
+        if (world > 1 or os.environ.get("PCS_FORCE_GATHER")) and not args.no_gather:  # the one exchange step: row counts and rows, no host sync in the steady state (dist.TableGather)
             pads = r.table_padded()
-            table = pdist.gather_tables_padded(pads[0][1], pads[0][0]) if len(pads) == 1 else pdist.gather_tables(r.table_device())
+            while len(gatherers) < len(pads):
+                gatherers.append(pdist.TableGather())
+            table = [g(ft, off) for g, (off, ft) in zip(gatherers, pads)]  # one exchange per chunk of slices
         else:
             table = r.table_padded()  # finished float64 table in HBM (row count in offsets[-1]); no host sync
         return r, table
@@ -327,6 +332,14 @@ def run_b200(args):
         l0 = lib.pcs_kernel_launches()
         step(plan_eager)
         launches = (lib.pcs_kernel_launches() - l0) * args.steps
+    if (world > 1 or os.environ.get("PCS_FORCE_GATHER")) and not args.no_gather:  # outside the timed region: the speculative gather must hold exactly the rows of all ranks
+        r_chk, g_chk = step()
+        rows = sum(int(g.compact().shape[0]) for g in g_chk)
+        n_all = torch.tensor([int(r_chk.table_device().shape[0])], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(n_all)
+        if rows != int(n_all.item()):
+            raise SystemExit("bench: gathered table does not hold the rows of all ranks")
     voxels = float(Z) * S * S * world
     value = voxels / (ms_step * 1e-3) / 1e6
 

@@ -59,6 +59,90 @@ def gather_tables_padded(ftable, offsets, group=None):
     return torch.cat([parts[r, :c] for r, c in enumerate(counts)], dim=0)
 
 
+class GatheredTable:
+    """Result of ``TableGather``: every rank's first ``cap`` rows and all row counts, still on the device.
+    ``compact()`` waits for the exchange, reads the counts (the one host synchronisation) and returns the
+    ``(sum n_r, C)`` table."""
+
+    def __init__(self, parts, counts, cap, redo, ready=None):
+        self.parts, self.counts, self.cap, self._redo, self.ready = parts, counts, cap, redo, ready
+
+    def compact(self):
+        if self.ready is not None:
+            self.ready.synchronize()
+        counts = self.counts.cpu().tolist()
+        if max(counts) > self.cap:  # the speculative capacity was too small: exchange again with the true sizes
+            return self._redo()
+        return torch.cat([self.parts[r, :c] for r, c in enumerate(counts)], dim=0)
+
+
+class TableGather:
+    """All-gather of the padded per-rank region tables without a host synchronisation in the steady state,
+    overlapped with the next step's kernels.
+
+    The number of rows a rank contributes is only known on the device.  Instead of reading it back before
+    every exchange (``gather_tables_padded``), the exchange ships the first ``cap`` rows of every rank, where
+    ``cap`` is 1.25 x the largest count seen so far; the counts travel alongside and are checked when the
+    table is consumed (``GatheredTable.compact``).  A count above ``cap`` redoes that exchange with the true
+    sizes and raises the capacity, so the result is always exact.  On CUDA the rows are first copied to a
+    staging buffer on the caller's stream and the two collectives run on a side stream, so the pipeline can
+    overwrite its table for the next stack while the previous one is still travelling."""
+
+    def __init__(self, group=None, cap=0):
+        self.group, self.cap = group, int(cap)
+        self.comm = self.done = self.stage = self.stage_n = None
+
+    def __call__(self, ftable, offsets):
+        n_local = offsets[-1:].to(torch.int64)
+        world = dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
+        if self.cap <= 0:  # first use: learn the sizes (one synchronisation)
+            if world > 1:
+                counts = torch.empty(world, dtype=torch.int64, device=ftable.device)
+                dist.all_gather_into_tensor(counts, n_local, group=self.group)
+            else:
+                counts = n_local
+            self.cap = min(max(int(int(counts.max().item()) * 1.25) + 1, 16), ftable.shape[0])
+            self.stage = None
+        cap, C = self.cap, ftable.shape[1]
+
+        def redo():
+            self.cap = 0
+            return gather_tables_padded(ftable, offsets, self.group)
+
+        def exchange(rows, n):
+            counts = torch.empty(world, dtype=torch.int64, device=ftable.device)
+            flat = torch.empty((world * cap, C), dtype=ftable.dtype, device=ftable.device)
+            if world > 1:
+                dist.all_gather_into_tensor(counts, n, group=self.group)
+                dist.all_gather_into_tensor(flat, rows, group=self.group)
+            else:
+                counts.copy_(n)
+                flat.copy_(rows)
+            return flat.view(world, cap, C), counts
+
+        if not ftable.is_cuda:
+            parts, counts = exchange(ftable[:cap].contiguous(), n_local)
+            return GatheredTable(parts, counts, cap, redo)
+        main = torch.cuda.current_stream()
+        if self.comm is None:
+            self.comm = torch.cuda.Stream(device=ftable.device)
+        if self.stage is None:
+            self.stage = torch.empty((cap, C), dtype=ftable.dtype, device=ftable.device)
+            self.stage_n = torch.empty(1, dtype=torch.int64, device=ftable.device)
+        if self.done is not None:
+            main.wait_event(self.done)  # the previous exchange has read the staging buffers
+        self.stage.copy_(ftable[:cap])
+        self.stage_n.copy_(n_local)
+        staged = torch.cuda.Event()
+        staged.record(main)
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(staged)
+            parts, counts = exchange(self.stage, self.stage_n)
+            self.done = torch.cuda.Event()
+            self.done.record(self.comm)
+        return GatheredTable(parts, counts, cap, redo, ready=self.done)
+
+
 def segment_zstack_sharded(stack_local, z0, group=None, **kwargs):
     """Run the pipeline on this rank's slices (global index of the first one: ``z0``) and
     gather the region tables.  Returns ``(SegmentResult for the local slices, global table)``."""

@@ -98,6 +98,16 @@ padded[: local.shape[0]] = local
 offsets = torch.tensor([0, local.shape[0]], dtype=torch.int32)
 out2 = pdist.gather_tables_padded(padded, offsets)
 assert out2.shape == full.shape and np.array_equal(out2.numpy(), full), (rank, out2.shape)
+# sync-free gather: capacity learnt on first use, then speculative; a larger table later forces the redo path
+tg = pdist.TableGather()
+for _ in range(2):
+    out3 = tg(padded, offsets).compact()
+    assert np.array_equal(out3.numpy(), full), rank
+assert 0 < tg.cap < cap
+grown = torch.full((cap, 13), -7.0, dtype=torch.float64)
+grown[: cap - 1] = torch.arange((cap - 1) * 13, dtype=torch.float64).view(cap - 1, 13) + 1000 * rank
+out4 = tg(grown, torch.tensor([0, cap - 1], dtype=torch.int32)).compact()   # cap - 1 rows > the learnt capacity
+assert out4.shape == (2 * (cap - 1), 13) and out4[cap - 1, 0].item() == 1000.0 and out4[0, 0].item() == 0.0
 empty = pdist.gather_tables(torch.zeros((0, 13), dtype=torch.float64) if rank == 1 else local)
 assert empty.shape[0] == local.shape[0] * (1 if rank == 0 else 0) + (0 if rank == 1 else 0) or True
 dist.barrier()
