@@ -167,6 +167,17 @@ int pcs_nearest_f64(const double* a, int64_t na, const double* b, int64_t nb, in
 /* out[i] = min_j |a_i - b_j| for (x, y) float64 pairs (pdist2 + min, .m:260-263, :301-304) */
 int pcs_min_dist_f64(const double* a, int64_t na, const double* b, int64_t nb, double* out, void* stream);
 
+/* ---- marker-controlled watershed ----------------------------------------------------------------
+ * skimage.segmentation.watershed(image, markers, mask=mask) with connectivity 1, compactness 0, no line
+ * (refine_boundaries.py:73): every pixel joins the 4-neighbour of smallest bottleneck cost, computed by
+ * tiled relaxation (pcs_watershed.cu).  Bit-identical to the sequential flood on tie-free images.
+ * image float64, markers int32 (> 0 = seed; seeds outside the mask are dropped), mask_bits optional bit
+ * image, labels int32 out.  BLOCKING (reads a convergence flag per sweep); max_sweeps <= 0 picks a bound
+ * from the image size; sweeps_out (host int, optional) receives the number of sweeps. */
+size_t pcs_watershed_workspace_bytes(int B, int H, int W);
+int pcs_watershed_f64(const double* image, const int32_t* markers, const uint32_t* mask_bits, int32_t* labels, int B, int H, int W,
+                      int max_sweeps, int* sweeps_out, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- NanoSIMS ratio images (.m:17-69) --------------------------------------------------------
  * imgaussfilt(A, sigma): taps 2*ceil(2*sigma)+1, replicate border, columns then rows, float64; tmp is
  * scratch of the same size as the images */

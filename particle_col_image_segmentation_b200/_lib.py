@@ -70,6 +70,8 @@ SIGNATURES = {
     "pcs_roi_sums_f64": (c_int, [_P, _P, _I, _L, _I, _P, _P]),
     "pcs_min_dist_f64": (c_int, [_P, _L, _P, _L, _P, _P]),
     "pcs_nearest_f64": (c_int, [_P, _L, _P, _L, _I, _P, _P, _P]),
+    "pcs_watershed_workspace_bytes": (_Z, [_I, _I, _I]),
+    "pcs_watershed_f64": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _Z, _P]),
     "pcs_gauss_f64": (c_int, [_P, _P, _P, c_double, _I, _I, _I, _P]),
     "pcs_ratio_f64": (c_int, [_P, _P, _P, _P, _P, _P, _L, _P]),
     "pcs_scale_u8_f64": (c_int, [_P, _P, _P, _L, _P]),

@@ -113,6 +113,24 @@ def test_config3_touching_particles_4096(mods):
     crop = mods.rb.refine_boundaries(np.ascontiguousarray(prob[:1024, :1024]))
     for k in ("binary_mask", "distance", "local_max", "markers"):
         assert np.array_equal(crop[k], want[k]), k
+    # the watershed (refine_boundaries.py:73) at full size: a valid flood of the whole mask from the markers
+    from particle_col_image_segmentation_b200 import segmentation
+
+    labels, sweeps = segmentation.watershed(prob, got["markers"], mask=binary_mask, return_sweeps=True)
+    assert labels.dtype == np.int32 and sweeps >= 1
+    assert np.array_equal(labels[got["markers"] > 0], got["markers"][got["markers"] > 0])
+    assert (labels[~binary_mask] == 0).all()
+    comp_has_marker = np.zeros(n + 1, bool)
+    lab4, n4 = ndi.label(binary_mask)  # 4-connected: the flood's connectivity
+    comp_has_marker = np.zeros(n4 + 1, bool)
+    comp_has_marker[np.unique(lab4[got["markers"] > 0])] = True
+    assert np.array_equal(labels != 0, comp_has_marker[lab4] & binary_mask)  # flooded = mask components holding a marker
+    same = np.zeros(labels.shape, bool)
+    same[1:] |= labels[1:] == labels[:-1]
+    same[:-1] |= labels[:-1] == labels[1:]
+    same[:, 1:] |= labels[:, 1:] == labels[:, :-1]
+    same[:, :-1] |= labels[:, :-1] == labels[:, 1:]
+    assert (same | (got["markers"] > 0) | (labels == 0)).all()  # every flooded pixel hangs on a neighbour of its label
 
 
 def test_class_image_2048_single_file_path(mods):
