@@ -21,55 +21,94 @@
 #define HIST_PIX_PER_BLOCK (HIST_THREADS * HIST_VEC_PER_THREAD * 8)  // 57344 < 65536
 #define HIST_SMEM_BYTES (32768 * 4)
 
+__device__ __forceinline__ void hist_count8(uint32_t* sh, const uint4& q) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t a = w[j] & 0xffffu, c = w[j] >> 16;
+    atomicAdd(&sh[a >> 1], 1u << ((a & 1u) << 4));
+    atomicAdd(&sh[c >> 1], 1u << ((c & 1u) << 4));
+  }
+}
+
+// CTA = `tiles` consecutive tiles of HIST_PIX_PER_BLOCK pixels of one slice.
+//  * The pixels of tile t + 1 are requested while tile t is being counted: as soon as a vector has been
+//    counted its registers receive the same vector of the next tile, so the HBM round trip hides behind the
+//    remaining atomics (the first version loaded and counted vector by vector and mostly waited for loads).
+//  * The packed counters are flushed only when one of them could overflow during the next tile, i.e. when
+//    some counter has reached 65536 - HIST_PIX_PER_BLOCK = 8192 (a one-instruction test per word while
+//    scanning shared memory), and at the end.  On micrographs the fullest bin takes < 1 % of the pixels, so a
+//    CTA flushes once instead of once per tile; an image of one value still flushes every tile and stays exact.
 __global__ void __launch_bounds__(HIST_THREADS, 1)
-    k_hist_u16(const uint16_t* __restrict__ img, uint32_t* __restrict__ hist, long long npix) {
+    k_hist_u16(const uint16_t* __restrict__ img, uint32_t* __restrict__ hist, long long npix, int tiles) {
   extern __shared__ uint32_t sh[];  // 32768 words, two 16-bit counters each
   const int tid = threadIdx.x;
   uint4* sh4 = reinterpret_cast<uint4*>(sh);
 #pragma unroll
   for (int i = 0; i < 32768 / 4 / HIST_THREADS; ++i) sh4[tid + i * HIST_THREADS] = make_uint4(0, 0, 0, 0);
-  __syncthreads();
   const long long b = blockIdx.y;
   const uint16_t* src = img + b * npix;
-  long long start = (long long)blockIdx.x * HIST_PIX_PER_BLOCK;
-  long long end = min(npix, start + (long long)HIST_PIX_PER_BLOCK);
+  uint32_t* g = hist + b * 65536;
   const bool aligned = ((((uintptr_t)src) & 15) == 0);
+  const long long start0 = (long long)blockIdx.x * tiles * HIST_PIX_PER_BLOCK;
+  auto full_tile = [&](long long start) { return aligned && start + HIST_PIX_PER_BLOCK <= npix; };
+  uint4 cur[HIST_VEC_PER_THREAD];
+  if (start0 < npix && full_tile(start0)) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(src + start0) + tid;
 #pragma unroll
-  for (int v = 0; v < HIST_VEC_PER_THREAD; ++v) {
-    long long i = start + ((long long)v * HIST_THREADS + tid) * 8;
-    if (i >= end) break;
-    if (aligned && i + 8 <= end) {
-      uint4 q = __ldg(reinterpret_cast<const uint4*>(src + i));
-      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint32_t a = w[j] & 0xffffu, c = w[j] >> 16;
-        atomicAdd(&sh[a >> 1], 1u << ((a & 1u) << 4));
-        atomicAdd(&sh[c >> 1], 1u << ((c & 1u) << 4));
-      }
-    } else {
-      for (long long j = i; j < min(end, i + 8); ++j) {
-        uint32_t a = src[j];
-        atomicAdd(&sh[a >> 1], 1u << ((a & 1u) << 4));
-      }
-    }
+    for (int v = 0; v < HIST_VEC_PER_THREAD; ++v) cur[v] = __ldg(s4 + v * HIST_THREADS);
   }
   __syncthreads();
-  uint32_t* g = hist + b * 65536;
+  for (int t = 0; t < tiles; ++t) {
+    const long long start = start0 + (long long)t * HIST_PIX_PER_BLOCK;
+    if (start >= npix) break;
+    const long long next = start + HIST_PIX_PER_BLOCK;
+    const bool have_next = t + 1 < tiles && next < npix && full_tile(next);
+    if (full_tile(start)) {
+      const uint4* n4 = reinterpret_cast<const uint4*>(src + next) + tid;
 #pragma unroll
-  for (int i = 0; i < 32768 / 4 / HIST_THREADS; ++i) {
-    int idx = tid + i * HIST_THREADS;
-    uint4 q = sh4[idx];
-    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (w[j]) {
-        int bin = (idx * 4 + j) * 2;
-        uint32_t lo = w[j] & 0xffffu, hi = w[j] >> 16;
-        if (lo) atomicAdd(g + bin, lo);
-        if (hi) atomicAdd(g + bin + 1, hi);
+      for (int v = 0; v < HIST_VEC_PER_THREAD; ++v) {
+        hist_count8(sh, cur[v]);
+        if (have_next) cur[v] = __ldg(n4 + v * HIST_THREADS);
+      }
+    } else {  // ragged tail or unaligned slice
+      const long long end = min(npix, next);
+      for (long long i = start + tid; i < end; i += HIST_THREADS) {
+        const uint32_t a = src[i];
+        atomicAdd(&sh[a >> 1], 1u << ((a & 1u) << 4));
       }
     }
+    __syncthreads();
+    const bool last = t + 1 >= tiles || next >= npix;
+    int hot = 0;  // some counter at 8192 or above: the next tile could overflow it
+    if (!last) {
+#pragma unroll
+      for (int i = 0; i < 32768 / 4 / HIST_THREADS; ++i) {
+        const uint4 q = sh4[tid + i * HIST_THREADS];
+        hot |= ((q.x | q.y | q.z | q.w) & 0xE000E000u) != 0u;
+      }
+    }
+    if (!__syncthreads_or(hot | (int)last)) continue;
+    // flush the non-zero counters and clear them
+#pragma unroll
+    for (int i = 0; i < 32768 / 4 / HIST_THREADS; ++i) {
+      const int idx = tid + i * HIST_THREADS;
+      const uint4 q = sh4[idx];
+      if (q.x | q.y | q.z | q.w) {
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (w[j]) {
+            const int bin = (idx * 4 + j) * 2;
+            const uint32_t lo = w[j] & 0xffffu, hi = w[j] >> 16;
+            if (lo) atomicAdd(g + bin, lo);
+            if (hi) atomicAdd(g + bin + 1, hi);
+          }
+        }
+        sh4[idx] = make_uint4(0, 0, 0, 0);
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -219,8 +258,20 @@ int pcs_histogram_u16(const uint16_t* img, uint32_t* hist, int B, int H, int W, 
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(hist, 0, pcs_histogram_bytes(B), st);
   long long npix = (long long)H * W;
-  dim3 grid((unsigned)((npix + HIST_PIX_PER_BLOCK - 1) / HIST_PIX_PER_BLOCK), B);
-  PCS_LAUNCH("k_hist_u16", st, k_hist_u16<<<grid, HIST_THREADS, HIST_SMEM_BYTES, st>>>(img, hist, npix));
+  // a few consecutive tiles per CTA so that the next tile's loads overlap the current tile's atomics and
+  // flush, and one flush serves several tiles; about four CTAs per SM overall keeps the tail short
+  const long long ntiles = (npix + HIST_PIX_PER_BLOCK - 1) / HIST_PIX_PER_BLOCK;
+  int sms = 148;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  long long per = (ntiles * B + 4LL * sms - 1) / (4LL * sms);
+  if (per < 1) per = 1;
+  if (per > ntiles) per = ntiles;
+  dim3 grid((unsigned)((ntiles + per - 1) / per), B);
+  PCS_LAUNCH("k_hist_u16", st, k_hist_u16<<<grid, HIST_THREADS, HIST_SMEM_BYTES, st>>>(img, hist, npix, (int)per));
   return pcs_check_launch("histogram");
 }
 
