@@ -398,10 +398,11 @@ __global__ void __launch_bounds__(PCS_CCL_THREADS)
   const int ch = g32 % CPR, y = g32 / CPR;
   int k = ch * 32 + lane;
   uint32_t roots = k < WW ? rootbits[(b * H + y) * (long long)WW + k] : 0u;
+  const int cbase = chunk[g];  // requested beside the root bits, not after the scan
   int tot;
   int ex = pcs_warp_excl_scan(__popc(roots), lane, &tot);
   if (!roots) return;
-  int rank = chunk[g] + ex;
+  int rank = cbase + ex;
   const int Wp = WW << 5;
   int* par = parent + b * (long long)H * Wp;
   int base = y * Wp + (k << 5);
@@ -528,37 +529,49 @@ __global__ void __launch_bounds__(PCS_CCL_THREADS)
 template <class P>
 __global__ void __launch_bounds__(PCS_CCL_THREADS)
     k_ccl_mark(P prov, int* __restrict__ parent, const uint32_t* __restrict__ m, int mode, int B) {
+  // thread per group of 4 words of a row: the four word loads are independent, and on the sparse planes
+  // this kernel usually sees (hole candidates, seeds) most groups leave right after them
   const int H = prov.H, WW = prov.WW, W = prov.W;
-  const int t32 = blockIdx.x * blockDim.x + threadIdx.x;  // word of the slice; the slice is blockIdx.y
-  if (t32 >= H * WW) return;
+  const int WG = (WW + 3) >> 2;
+  const int g32 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g32 >= H * WG) return;
   const long long b = blockIdx.y;
-  const long long t = b * H * WW + t32;
-  const int k = t32 % WW, y = t32 / WW;
+  const int y = g32 / WG, k0 = (g32 % WG) << 2;
   P p = prov.slice(b);
-  uint32_t F, S;
-  p.FS(y, k, F, S);
-  if (!S) return;
-  uint32_t M;
-  if (mode == 0) {
-    M = (y == 0 || y == H - 1) ? 0xffffffffu : 0u;
-    if (k == 0) M |= 1u;
-    if (k == WW - 1) M |= 1u << ((W - 1) & 31);
-  } else {
-    M = m[t];
+  uint32_t F4[4], S4[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    F4[i] = S4[i] = 0u;
+    if (k0 + i < WW) p.FS(y, k0 + i, F4[i], S4[i]);
   }
-  M &= F;
-  if (!M) return;
+  if (!(S4[0] | S4[1] | S4[2] | S4[3])) return;
   const int Wp = WW << 5;
   int* par = parent + b * (long long)H * Wp;
-  int base = y * Wp + (k << 5);
-  while (S) {
-    int s;
-    uint32_t R = pcs_pop_run(F, S, s);
-    if (!(R & M)) continue;
-    int n = base + s;
-    int q = par[n];
-    if (q < 0) continue;  // already a marked root
-    par[q] = PCS_MARK;     // q is the root (q == n for a root)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t F = F4[i], S = S4[i];
+    if (!S) continue;
+    const int k = k0 + i;
+    uint32_t M;
+    if (mode == 0) {
+      M = (y == 0 || y == H - 1) ? 0xffffffffu : 0u;
+      if (k == 0) M |= 1u;
+      if (k == WW - 1) M |= 1u << ((W - 1) & 31);
+    } else {
+      M = m[(b * H + y) * (long long)WW + k];
+    }
+    M &= F;
+    if (!M) continue;
+    const int base = y * Wp + (k << 5);
+    while (S) {
+      int s;
+      uint32_t R = pcs_pop_run(F, S, s);
+      if (!(R & M)) continue;
+      int n = base + s;
+      int q = par[n];
+      if (q < 0) continue;  // already a marked root
+      par[q] = PCS_MARK;     // q is the root (q == n for a root)
+    }
   }
 }
 
@@ -838,18 +851,27 @@ __global__ void __launch_bounds__(REFINE_MAX_WARPS * 32)
   }
 }
 
-// thread per word: seeds = candidate pixels on the top / bottom image row or 4-adjacent to background
-// that is not a candidate (such background is never part of a hole)
+// thread per group of 4 words: seeds = candidate pixels on the top / bottom image row or 4-adjacent to
+// background that is not a candidate (such background is never part of a hole).  Only words that hold
+// candidates are written: k_ccl_mark reads the seed plane nowhere else.
 __global__ void __launch_bounds__(256)
     k_hole_seeds(const uint32_t* __restrict__ kept, const uint32_t* __restrict__ cand, uint32_t* __restrict__ seed, int B, int H,
                  int W, int WW) {
-  const int t32 = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t32 >= H * WW) return;
-  const long long t = (long long)blockIdx.y * H * WW + t32;
-  const uint32_t C = cand[t];
-  uint32_t M = 0;
-  if (C) {
-    const int k = t32 % WW, y = t32 / WW;
+  const int WG = (WW + 3) >> 2;
+  const int g32 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g32 >= H * WG) return;
+  const int y = g32 / WG, k0 = (g32 % WG) << 2;
+  const long long t0 = ((long long)blockIdx.y * H + y) * WW + k0;
+  uint32_t C4[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) C4[i] = k0 + i < WW ? __ldg(cand + t0 + i) : 0u;
+  if (!(C4[0] | C4[1] | C4[2] | C4[3])) return;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t C = C4[i];
+    if (!C) continue;
+    const int k = k0 + i;
+    const long long t = t0 + i;
     auto open_at = [&](long long idx, int kk) { return ~kept[idx] & ~cand[idx] & pcs_valid_mask(kk, W); };
     const uint32_t n_c = open_at(t, k);
     uint32_t adj = (n_c << 1) | (n_c >> 1);
@@ -858,9 +880,8 @@ __global__ void __launch_bounds__(256)
     adj |= (y > 0) ? open_at(t - WW, k) : 0xffffffffu;
     adj |= (y + 1 < H) ? open_at(t + WW, k) : 0xffffffffu;
     adj |= 1u << ((W - 1) & 31) & ((k == WW - 1) ? 0xffffffffu : 0u);  // right image border
-    M = C & adj;
+    seed[t] = C & adj;
   }
-  seed[t] = M;
 }
 
 // ============================================================== host drivers
@@ -869,6 +890,7 @@ static int ccl_forest(const P& prov, int B, int conn, const PcsCclWs& ws, int32_
   const int H = prov.H, WW = prov.WW;
   const int CPR = (WW + 31) / 32;
   dim3 gw(pcs_blocks((long long)H * WW, PCS_CCL_THREADS), B);
+  dim3 gq(pcs_blocks((long long)H * ((WW + 3) / 4), PCS_CCL_THREADS), B);  // groups of 4 words
   dim3 gc(pcs_blocks((long long)H * CPR * 32, PCS_CCL_THREADS), B);
   constexpr int CCL_TR = PcsTile<P>::TR, TW = PcsTile<P>::TW;
   PCS_REQUIRE(B <= 65535 && (H + CCL_TR - 1) / CCL_TR <= 65535, "grid too large for the tile kernel");
@@ -955,7 +977,8 @@ int pcs_fill_holes_bits(const uint32_t* bits, uint32_t* out, int B, int H, int W
   rc = ccl_forest(prov, B, 4, ws, nullptr, 0, st);
   if (rc) return rc;
   dim3 gw(pcs_blocks((long long)H * prov.WW, PCS_CCL_THREADS), B);
-  PCS_LAUNCH("k_ccl_mark", st, k_ccl_mark<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, nullptr, 0, B));
+  dim3 gq(pcs_blocks((long long)H * ((prov.WW + 3) / 4), PCS_CCL_THREADS), B);  // groups of 4 words
+  PCS_LAUNCH("k_ccl_mark", st, k_ccl_mark<PcsBinProv><<<gq, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, nullptr, 0, B));
   PCS_LAUNCH("k_ccl_select", st, k_ccl_select<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, 0, bits, nullptr, out, nullptr, B));
   return pcs_check_launch("fill holes");
 }
@@ -983,11 +1006,12 @@ int pcs_fill_holes_table_bits(const uint32_t* bits, const int64_t* table, int64_
   cudaMemsetAsync(bb, 0, (size_t)B * H * WW * 4, st);
   PCS_LAUNCH("k_bbox_raster", st, k_bbox_raster<<<pcs_blocks(cap * 32, 256), 256, 0, st>>>((const long long*)table, cap, offsets, min_size, bb, B, H, WW));
   dim3 gw(pcs_blocks((long long)H * WW, PCS_CCL_THREADS), B);
+  dim3 gq(pcs_blocks((long long)H * ((WW + 3) / 4), PCS_CCL_THREADS), B);  // groups of 4 words
   PCS_LAUNCH("k_hole_candidates", st, k_hole_candidates<<<gw, 256, 0, st>>>(bits, bb, cand, seed, B, H, W, WW));
   PcsBinProv prov{cand, H, W, WW, 0};
   rc = ccl_forest(prov, B, 4, ws, nullptr, 0, st);
   if (rc) return rc;
-  PCS_LAUNCH("k_ccl_mark", st, (k_ccl_mark<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, seed, 1, B)));
+  PCS_LAUNCH("k_ccl_mark", st, (k_ccl_mark<PcsBinProv><<<gq, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, seed, 1, B)));
   PCS_LAUNCH("k_ccl_select", st, (k_ccl_select<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, 0, bits, nullptr, out, out_mask, B)));
   return pcs_check_launch("fill holes (table)");
 }
@@ -1026,11 +1050,12 @@ int pcs_refine_labeled_bits(const uint32_t* bits, const int32_t* labels, const i
   PCS_LAUNCH("k_refine_rows", st, (k_refine_rows<<<pcs_blocks(rows, warps), warps * 32, warps * warp_bytes, st>>>(
       bits, labels, (const long long*)table, cap, offsets, min_size, kept, cand, rows, H, W, WW)));
   dim3 gw(pcs_blocks((long long)H * WW, PCS_CCL_THREADS), B);
-  PCS_LAUNCH("k_hole_seeds", st, (k_hole_seeds<<<gw, 256, 0, st>>>(kept, cand, seed, B, H, W, WW)));
+  dim3 gq(pcs_blocks((long long)H * ((WW + 3) / 4), PCS_CCL_THREADS), B);  // groups of 4 words
+  PCS_LAUNCH("k_hole_seeds", st, (k_hole_seeds<<<dim3(pcs_blocks((long long)H * ((WW + 3) / 4), 256), B), 256, 0, st>>>(kept, cand, seed, B, H, W, WW)));
   PcsBinProv prov{cand, H, W, WW, 0};
   rc = ccl_forest(prov, B, 4, ws, nullptr, 0, st);
   if (rc) return rc;
-  PCS_LAUNCH("k_ccl_mark", st, (k_ccl_mark<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, seed, 1, B)));
+  PCS_LAUNCH("k_ccl_mark", st, (k_ccl_mark<PcsBinProv><<<gq, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, seed, 1, B)));
   PCS_LAUNCH("k_ccl_select", st, (k_ccl_select<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, 0, kept, nullptr, out, out_mask, B)));
   return pcs_check_launch("refine (labelled)");
 }
@@ -1052,6 +1077,7 @@ int pcs_remove_small_bits(const uint32_t* bits, uint32_t* out, int B, int H, int
   rc = ccl_forest(prov, B, connectivity, ws, nullptr, 1, st);
   if (rc) return rc;
   dim3 gw(pcs_blocks((long long)H * prov.WW, PCS_CCL_THREADS), B);
+  dim3 gq(pcs_blocks((long long)H * ((prov.WW + 3) / 4), PCS_CCL_THREADS), B);  // groups of 4 words
   PCS_LAUNCH("k_ccl_area", st, k_ccl_area<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, ws.aux, B));
   PCS_LAUNCH("k_ccl_mark_small", st, k_ccl_mark_small<<<gw, PCS_CCL_THREADS, 0, st>>>(ws.parent, ws.rootbits, ws.aux, min_size, B, H, prov.WW));
   PCS_LAUNCH("k_ccl_select", st, k_ccl_select<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, 0, nullptr, nullptr, out, nullptr, B));
@@ -1071,7 +1097,8 @@ int pcs_select_components_bits(const uint32_t* bits, const uint32_t* seeds, uint
   rc = ccl_forest(prov, B, connectivity, ws, nullptr, 0, st);
   if (rc) return rc;
   dim3 gw(pcs_blocks((long long)H * prov.WW, PCS_CCL_THREADS), B);
-  PCS_LAUNCH("k_ccl_mark", st, k_ccl_mark<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, seeds, 1, B));
+  dim3 gq(pcs_blocks((long long)H * ((prov.WW + 3) / 4), PCS_CCL_THREADS), B);  // groups of 4 words
+  PCS_LAUNCH("k_ccl_mark", st, k_ccl_mark<PcsBinProv><<<gq, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, seeds, 1, B));
   PCS_LAUNCH("k_ccl_select", st, k_ccl_select<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, 1, nullptr, nullptr, out, nullptr, B));
   return pcs_check_launch("select components");
 }
@@ -1090,7 +1117,8 @@ int pcs_local_maxima_conn(const uint32_t* planes, const uint32_t* higher, uint32
   rc = ccl_forest(prov, B, connectivity, ws, counts, 0, st);
   if (rc) return rc;
   dim3 gw(pcs_blocks((long long)H * prov.WW, PCS_CCL_THREADS), B);
-  PCS_LAUNCH("k_ccl_mark", st, k_ccl_mark<PcsGenProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, higher, 1, B));
+  dim3 gq(pcs_blocks((long long)H * ((prov.WW + 3) / 4), PCS_CCL_THREADS), B);  // groups of 4 words
+  PCS_LAUNCH("k_ccl_mark", st, k_ccl_mark<PcsGenProv><<<gq, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, higher, 1, B));
   // a plateau that is the whole image (counts == 1) is not a maximum
   PCS_LAUNCH("k_ccl_select", st, k_ccl_select<PcsGenProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, 0, nullptr, counts, out, nullptr, B));
   return pcs_check_launch("local maxima");

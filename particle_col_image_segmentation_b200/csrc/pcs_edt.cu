@@ -37,32 +37,44 @@
 #define EDT_KEY_MAX 0xFFFFFFFFFFFFFFFFull
 #define EDT_WARPS 8
 
-// warp per (slice, band, word): 32 rows x 32 columns of bits -> 32 vertical words
+// warp per (slice, band, group of 4 words): 32 rows x 128 columns of bits -> 128 vertical words.  Four
+// independent loads per lane are in flight before the shuffles start (one load per warp left the kernel
+// waiting on memory latency).
 __global__ void __launch_bounds__(256)
     k_edt_transpose(const uint32_t* __restrict__ bits, int invert, uint32_t* __restrict__ vw, int B, int H, int W, int WW,
                     int NB) {
   long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  long long total = (long long)B * NB * WW;
+  const int WG = (WW + 3) >> 2;
+  long long total = (long long)B * NB * WG;
   if (g >= total) return;
-  int k, q;
+  int kg, q;
   long long b;
-  pcs_split3(g, WW, NB, k, q, b);
+  pcs_split3(g, WG, NB, kg, q, b);
   const int y = (q << 5) + lane;
-  uint32_t w = 0xffffffffu;  // rows past the image never act as background
-  if (y < H) {
-    w = bits[(b * H + y) * (long long)WW + k];
-    if (invert) w = ~w;
+  const int k0 = kg << 2;
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    w[i] = 0xffffffffu;  // rows past the image never act as background
+    if (y < H && k0 + i < WW) {
+      w[i] = __ldg(bits + (b * H + y) * (long long)WW + k0 + i);
+      if (invert) w[i] = ~w[i];
+    }
   }
-  // 32x32 bit transpose across the warp: five block-swap steps (lane = row in, lane = column out)
+  // 32x32 bit transposes across the warp: five block-swap steps (lane = row in, lane = column out)
 #pragma unroll
   for (int j = 16; j >= 1; j >>= 1) {
     const uint32_t m = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu : j == 2 ? 0x33333333u : 0x55555555u;
-    const uint32_t other = __shfl_xor_sync(0xffffffffu, w, j);
-    w = (lane & j) ? ((w & ~m) | ((other & ~m) >> j)) : ((w & m) | ((other & m) << j));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t other = __shfl_xor_sync(0xffffffffu, w[i], j);
+      w[i] = (lane & j) ? ((w[i] & ~m) | ((other & ~m) >> j)) : ((w[i] & m) | ((other & m) << j));
+    }
   }
-  const uint32_t mine = w;
-  vw[(b * NB + q) * (long long)(WW << 5) + (k << 5) + lane] = mine;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (k0 + i < WW) vw[(b * NB + q) * (long long)(WW << 5) + ((k0 + i) << 5) + lane] = w[i];
 }
 
 // thread per (column, direction): distance from the band edge to the nearest background row beyond it.
@@ -424,7 +436,7 @@ int pcs_edt_bits(const uint32_t* bits, int invert, int B, int H, int W, double* 
   uint8_t* row_far = (uint8_t*)p;
   cudaMemsetAsync(row_far, 0, (size_t)B * H, st);
   PCS_LAUNCH("k_edt_transpose", st,
-             k_edt_transpose<<<pcs_blocks((long long)B * NB * WW * 32, 256), 256, 0, st>>>(bits, invert, vw, B, H, W, WW, NB));
+             k_edt_transpose<<<pcs_blocks((long long)B * NB * ((WW + 3) / 4) * 32, 256), 256, 0, st>>>(bits, invert, vw, B, H, W, WW, NB));
   dim3 gc((W + 127) / 128, B, 2);
   PCS_LAUNCH("k_edt_carry", st, k_edt_carry<<<gc, 128, 0, st>>>(vw, up, dn, W, Wp, NB));
   {

@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(1024) k_otsu_u16(const uint32_t* __restrict__ 
   const uint4* h4 = reinterpret_cast<const uint4*>(h + tid * 64);
   long long cnt = 0, sum = 0;
   int lo = 65536, hi = -1;
-#pragma unroll 4
+#pragma unroll 8
   for (int i = 0; i < 16; ++i) {
     uint4 q = __ldg(h4 + i);
     const uint32_t c[4] = {q.x, q.y, q.z, q.w};
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(1024) k_otsu_u16(const uint32_t* __restrict__ 
   long long run_cnt = s_cnt[wid] + (icnt - cnt);  // pixels strictly below this thread's first bin
   long long run_sum = s_sum[wid] + (isum - sum);
   OtsuBest best{0.0, -1};
-#pragma unroll 2
+#pragma unroll 4
   for (int i = 0; i < 16; ++i) {
     uint4 q = __ldg(h4 + i);  // second read of the 256 KB histogram hits L2
     const uint32_t c[4] = {q.x, q.y, q.z, q.w};
