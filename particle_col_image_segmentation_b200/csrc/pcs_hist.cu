@@ -207,7 +207,9 @@ __global__ void __launch_bounds__(1024) k_otsu_u16(const uint32_t* __restrict__ 
       int v = tid * 64 + 4 * i + j;
       run_cnt += c[j];
       run_sum += (long long)c[j] * v;
-      if (v >= vmin && v < vmax) {
+      // an empty bin leaves both classes as they were: its variance equals the previous bin's and can
+      // never be the FIRST maximum, so the (slow, fp64) evaluation is skipped for it
+      if (c[j] != 0u && v >= vmin && v < vmax) {
         float w1 = (float)run_cnt, w2 = (float)(tot_cnt - run_cnt);  // exact: npix <= 2^24
         double m1 = (double)run_sum / (double)w1;
         double m2 = (double)(tot_sum - run_sum) / (double)w2;
