@@ -105,12 +105,24 @@ __global__ void __launch_bounds__(CCL_TILE_THREADS) k_ccl_tile(P prov, int* __re
   P p = prov.slice(b);
   if (threadIdx.x == 0) nitems = 0;
   __syncthreads();
-  // phase A, thread per word: stage the tile, give every run its own slot, list the non-empty words
-  for (int w = threadIdx.x; w < NWORDS; w += CCL_TILE_THREADS) {
+  // phase A, thread per word: stage the tile, give every run its own slot, list the non-empty words.
+  // The words of all of a thread's iterations are requested first (one memory round trip, not one each).
+  constexpr int NPT = (NWORDS + CCL_TILE_THREADS - 1) / CCL_TILE_THREADS;
+  uint32_t Fpre[NPT], Spre[NPT];
+#pragma unroll
+  for (int i = 0; i < NPT; ++i) {
+    const int w = threadIdx.x + i * CCL_TILE_THREADS;
+    const int k = k0 + w % TW, y = y0 + w / TW;
+    Fpre[i] = Spre[i] = 0u;
+    if (w < NWORDS && y < H && k < WW) p.FS(y, k, Fpre[i], Spre[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < NPT; ++i) {
+    const int w = threadIdx.x + i * CCL_TILE_THREADS;
+    if (w >= NWORDS) break;
     const int r = w / TW, c = w % TW;
     const int k = k0 + c, y = y0 + r;
-    uint32_t F = 0, S = 0;
-    if (y < H && k < WW) p.FS(y, k, F, S);
+    uint32_t F = Fpre[i], S = Spre[i];
     fsm[w] = F;
     ssm[w] = S;
     if (!kBin) {
@@ -281,48 +293,77 @@ __global__ void __launch_bounds__(PCS_CCL_THREADS) k_ccl_merge_edges(P prov, int
   }
 }
 
-// warp per 32-word chunk: point every node at its root, flag roots, count them
+// warp per PAIR of 32-word chunks: point every node at its root, flag roots, count them.  A lane walks
+// the parent chains of its two words side by side, so two dependent load chains are in flight per lane
+// (the kernel is bound by that pointer chase).
 template <class P>
 __global__ void __launch_bounds__(PCS_CCL_THREADS)
     k_ccl_flatten(P prov, int* __restrict__ parent, uint32_t* __restrict__ rootbits, int* __restrict__ chunk,
                   int* __restrict__ aux, int B, int CPR) {
   const int H = prov.H, WW = prov.WW;
-  const int g32 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // 32-word chunk of the slice; the slice is blockIdx.y
+  const int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // pair of chunks of the slice; the slice is blockIdx.y
   int lane = threadIdx.x & 31;
-  if (g32 >= H * CPR) return;
+  const int nchunks = H * CPR;
+  if (2 * pair >= nchunks) return;
   const long long b = blockIdx.y;
-  const long long g = b * H * CPR + g32;
-  const int ch = g32 % CPR, y = g32 / CPR;
-  int k = ch * 32 + lane;
-  uint32_t roots = 0;
-  if (k < WW) {
-    P p = prov.slice(b);
-    uint32_t F, S;
-    p.FS(y, k, F, S);
-    const int Wp = WW << 5;
-    int* par = parent + b * (long long)H * Wp;
-    int base = y * Wp + (k << 5);
-    while (S) {
-      int s = __ffs(S) - 1;
-      S &= S - 1;
-      int n = base + s;
-      int r = n, q = pcs_ld_cg(par + r);
-      while (q != r) {
-        r = q;
-        q = pcs_ld_cg(par + r);
+  P p = prov.slice(b);
+  const int Wp = WW << 5;
+  int* par = parent + b * (long long)H * Wp;
+  uint32_t Sw[2] = {0u, 0u}, roots[2] = {0u, 0u};
+  int base[2] = {0, 0}, kk[2], yy[2];
+  bool valid[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int g32 = 2 * pair + u;
+    valid[u] = g32 < nchunks;
+    const int ch = g32 % CPR;
+    yy[u] = g32 / CPR;
+    kk[u] = ch * 32 + lane;
+    if (valid[u] && kk[u] < WW) {
+      uint32_t F;
+      p.FS(yy[u], kk[u], F, Sw[u]);
+      base[u] = yy[u] * Wp + (kk[u] << 5);
+    }
+  }
+  while (Sw[0] | Sw[1]) {
+    int n[2], r[2], q[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      n[u] = -1;
+      if (Sw[u]) {
+        const int s = __ffs(Sw[u]) - 1;
+        Sw[u] &= Sw[u] - 1;
+        n[u] = base[u] + s;
       }
-      if (r != n)
-        par[n] = r;
+      r[u] = n[u];
+      q[u] = n[u] >= 0 ? pcs_ld_cg(par + n[u]) : -1;
+    }
+    while (q[0] != r[0] || q[1] != r[1]) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+        if (q[u] != r[u]) {
+          r[u] = q[u];
+          q[u] = pcs_ld_cg(par + r[u]);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (n[u] < 0) continue;
+      if (r[u] != n[u])
+        par[n[u]] = r[u];
       else {
-        roots |= 1u << s;
-        if (aux) aux[b * (long long)H * Wp + n] = 0;
+        roots[u] |= 1u << (n[u] - base[u]);
+        if (aux) aux[b * (long long)H * Wp + n[u]] = 0;
       }
     }
-    rootbits[(b * H + y) * (long long)WW + k] = roots;
   }
-  int cnt = __popc(roots);
-  cnt = __reduce_add_sync(0xffffffffu, cnt);
-  if (lane == 0) chunk[g] = cnt;
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    if (!valid[u]) continue;  // warp-uniform
+    if (kk[u] < WW) rootbits[(b * H + yy[u]) * (long long)WW + kk[u]] = roots[u];
+    const int cnt = __reduce_add_sync(0xffffffffu, __popc(roots[u]));
+    if (lane == 0) chunk[b * (long long)nchunks + 2 * pair + u] = cnt;
+  }
 }
 
 // block per slice: exclusive scan of the chunk counts (raster order), slice total
@@ -905,7 +946,7 @@ static int ccl_forest(const P& prov, int B, int conn, const PcsCclWs& ws, int32_
     PCS_LAUNCH("k_ccl_tile", st, (k_ccl_tile<P, 4><<<gt, CCL_TILE_THREADS, 0, st>>>(prov, ws.parent)));
     PCS_LAUNCH("k_ccl_merge_edges", st, (k_ccl_merge_edges<P, 4><<<ge, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, B, per_slice)));
   }
-  PCS_LAUNCH("k_ccl_flatten", st, k_ccl_flatten<P><<<gc, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, ws.rootbits, ws.chunk, zero_aux ? ws.aux : nullptr, B, CPR));
+  PCS_LAUNCH("k_ccl_flatten", st, k_ccl_flatten<P><<<dim3(pcs_blocks(((long long)H * CPR + 1) / 2 * 32, PCS_CCL_THREADS), B), PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, ws.rootbits, ws.chunk, zero_aux ? ws.aux : nullptr, B, CPR));
   if (counts) {
     PCS_LAUNCH("k_ccl_scan", st, k_ccl_scan<<<B, 1024, 0, st>>>(ws.chunk, counts, H * CPR));
     PCS_LAUNCH("k_ccl_offsets", st, k_ccl_offsets<<<1, 1024, 0, st>>>(counts, ws.offsets, B));
@@ -1042,11 +1083,8 @@ int pcs_refine_labeled_bits(const uint32_t* bits, const int32_t* labels, const i
   int warps = (int)(REFINE_SMEM_LIMIT / warp_bytes);
   PCS_REQUIRE(warps >= 1, "row too wide for the refine kernel");
   if (warps > REFINE_MAX_WARPS) warps = REFINE_MAX_WARPS;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_refine_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, REFINE_SMEM_LIMIT);
-    attr_set = true;
-  }
+  static bool attr_set[64] = {};
+  if (pcs_first_use(attr_set)) cudaFuncSetAttribute(k_refine_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, REFINE_SMEM_LIMIT);
   PCS_LAUNCH("k_refine_rows", st, (k_refine_rows<<<pcs_blocks(rows, warps), warps * 32, warps * warp_bytes, st>>>(
       bits, labels, (const long long*)table, cap, offsets, min_size, kept, cand, rows, H, W, WW)));
   dim3 gw(pcs_blocks((long long)H * WW, PCS_CCL_THREADS), B);

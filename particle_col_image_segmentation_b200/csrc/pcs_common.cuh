@@ -39,6 +39,17 @@ void pcs_prof_end(cudaStream_t st);
   } while (0)
 
 static inline int pcs_words(int W) { return (W + 31) >> 5; }
+// true the first time it is called for (slot, current device): kernels that need a function attribute
+// (opt-in shared memory) set it once per device, so a process that drives several GPUs stays correct
+static inline bool pcs_first_use(bool (&done)[64]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return true;
+  if (done[dev]) return false;
+  done[dev] = true;
+  return true;
+}
+
 static inline size_t pcs_align256(size_t n) { return (n + 255) & ~(size_t)255; }
 static inline unsigned pcs_blocks(long long n, int per_block) {
   long long b = (n + per_block - 1) / per_block;

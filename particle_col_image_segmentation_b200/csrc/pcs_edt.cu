@@ -456,10 +456,14 @@ int pcs_edt_bits(const uint32_t* bits, int invert, int B, int H, int W, double* 
     W2 <<= 1;
     ++L;
   }
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    cudaFuncSetAttribute(k_edt_far, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    smem_set = smem;
+  static size_t smem_set[64] = {};  // per device: largest opt-in shared-memory size set so far
+  if (smem > 48 * 1024) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || smem > smem_set[dev]) {
+      cudaFuncSetAttribute(k_edt_far, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (dev >= 0 && dev < 64) smem_set[dev] = smem;
+    }
   }
   dim3 gf((H + nwarps - 1) / nwarps, B);
   PCS_LAUNCH("k_edt_far", st,

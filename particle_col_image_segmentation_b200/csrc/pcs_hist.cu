@@ -252,11 +252,8 @@ size_t pcs_histogram_bytes(int B) { return (size_t)B * 65536 * 4; }
 
 int pcs_histogram_u16(const uint16_t* img, uint32_t* hist, int B, int H, int W, void* stream) {
   PCS_REQUIRE(B >= 1 && H >= 1 && W >= 1, "empty batch or image");
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_hist_u16, cudaFuncAttributeMaxDynamicSharedMemorySize, HIST_SMEM_BYTES);
-    attr_set = true;
-  }
+  static bool attr_set[64] = {};
+  if (pcs_first_use(attr_set)) cudaFuncSetAttribute(k_hist_u16, cudaFuncAttributeMaxDynamicSharedMemorySize, HIST_SMEM_BYTES);
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(hist, 0, pcs_histogram_bytes(B), st);
   long long npix = (long long)H * W;

@@ -126,6 +126,24 @@ def test_otsu(pcs):
     assert thr.cpu().tolist() == [int(ofilters.threshold_otsu(s)) for s in st]
 
 
+def test_histogram_exact_when_counters_saturate(pcs):
+    """The histogram CTA walks several tiles and flushes its packed 16-bit counters only when one could
+    overflow during the next tile: images dominated by one or two values must force those flushes and stay
+    exact; odd sizes put later slices off 16-byte alignment (scalar path)."""
+    rng = np.random.default_rng(12)
+    for shape, hot in (((2, 1024, 1024), 0.7), ((1, 2048, 2048), 0.995), ((3, 333, 1001), 0.5), ((2, 2048, 2048), 0.0)):
+        st = rng.integers(0, 65536, shape).astype(np.uint16)
+        m = rng.random(shape) < hot
+        st[m] = 1000
+        st[m & (rng.random(shape) < 0.3)] = 1001  # the neighbour counter shares the 32-bit word with bin 1000
+        t = torch.from_numpy(st).cuda()
+        thr, hist = pcs.ops.otsu_u16(t, return_hist=True)
+        for i in range(shape[0]):
+            want = np.bincount(st[i].ravel(), minlength=65536)
+            assert np.array_equal(hist[i].cpu().numpy().astype(np.int64), want), (shape, hot, i)
+            assert int(thr[i]) == int(ofilters.threshold_otsu(st[i])), (shape, hot, i)
+
+
 # ---------------------------------------------------------------- K3
 @pytest.mark.parametrize("size", [3, 5, 7])
 def test_median_u8(pcs, size):
