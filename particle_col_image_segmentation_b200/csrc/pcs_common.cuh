@@ -112,9 +112,10 @@ __device__ __forceinline__ void pcs_store_mask_bytes(uint8_t* __restrict__ row, 
     uint32_t o[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      uint32_t n = (w >> (4 * i)) & 0xfu;
-      // spread 4 bits to 4 bytes
-      o[i] = (n & 1u) | ((n & 2u) << 7) | ((n & 4u) << 14) | ((n & 8u) << 21);
+      const uint32_t n = (w >> (4 * i)) & 0xfu;
+      // spread 4 bits to 4 bytes: n * (1 + 2^7 + 2^14 + 2^21) puts bit j at position 8j (no carries: the
+      // four shifted copies of a 4-bit value do not overlap), the mask keeps just those
+      o[i] = (n * 0x00204081u) & 0x01010101u;
     }
     uint4* dst = reinterpret_cast<uint4*>(row + x0);
     dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
