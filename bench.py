@@ -287,7 +287,7 @@ def run_b200(args):
 
     def step(p=None):
         r = (p or plan)()
-        if (world > 1 or os.environ.get("PCS_FORCE_GATHER")) and not args.no_gather:  # the one exchange step: row counts and rows, no host sync in the steady state (dist.TableGather)
+        if world > 1 and not args.no_gather:  # the one exchange step: row counts and rows, no host sync in the steady state (dist.TableGather)
             pads = r.table_padded()
             while len(gatherers) < len(pads):
                 gatherers.append(pdist.TableGather())
@@ -345,7 +345,7 @@ def run_b200(args):
         l0 = lib.pcs_kernel_launches()
         step(plan_eager)
         launches = (lib.pcs_kernel_launches() - l0) * args.steps
-    if (world > 1 or os.environ.get("PCS_FORCE_GATHER")) and not args.no_gather:  # outside the timed region: the speculative gather must hold exactly the rows of all ranks
+    if world > 1 and not args.no_gather:  # outside the timed region: the speculative gather must hold exactly the rows of all ranks
         r_chk, g_chk = step()
         rows = sum(int(g.compact().shape[0]) for g in g_chk)
         n_all = torch.tensor([int(r_chk.table_device().shape[0])], dtype=torch.int64, device=dev)
