@@ -217,6 +217,59 @@ __global__ void __launch_bounds__(MED_TX* MED_TY)
   out[b * (long long)H * W + (long long)y * W + x] = (uint8_t)v;
 }
 
+// ---------------------------------------------------------------- images smaller than the window
+// scipy's 'reflect' keeps folding an index until it lands inside the image ((d c b a | a b c d | d c b a)
+// repeated), which only matters when a side is shorter than the window.  These per-pixel kernels do the
+// general fold; they are only launched for such tiny images, where speed is irrelevant.
+__device__ __forceinline__ int pcs_reflect_any(int i, int n) {
+  const int p = 2 * n;
+  i %= p;
+  if (i < 0) i += p;
+  return i < n ? i : p - 1 - i;
+}
+
+__global__ void __launch_bounds__(256)
+    k_majority_small(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int size, int B, int H, int W, int WW) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // thread per output word
+  if (t >= (long long)B * H * WW) return;
+  int k, y;
+  long long b;
+  pcs_split3(t, WW, H, k, y, b);
+  const uint32_t* src = in + b * (long long)H * WW;
+  const int r = size >> 1, need = (size * size) / 2 + 1;
+  uint32_t o = 0;
+  for (int j = 0; j < 32 && (k << 5) + j < W; ++j) {
+    int cnt = 0;
+    for (int dy = -r; dy <= r; ++dy)
+      for (int dx = -r; dx <= r; ++dx) {
+        const int yy = pcs_reflect_any(y + dy, H), xx = pcs_reflect_any((k << 5) + j + dx, W);
+        cnt += (src[(long long)yy * WW + (xx >> 5)] >> (xx & 31)) & 1u;
+      }
+    o |= (uint32_t)(cnt >= need) << j;
+  }
+  out[t] = o;
+}
+
+__global__ void __launch_bounds__(256)
+    k_median_small(const uint8_t* __restrict__ img, uint8_t* __restrict__ out, int size, int B, int H, int W) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // thread per pixel
+  if (t >= (long long)B * H * W) return;
+  int x, y;
+  long long b;
+  pcs_split3(t, W, H, x, y, b);
+  const uint8_t* src = img + b * (long long)H * W;
+  const int r = size >> 1, rank = (size * size) / 2;
+  int v = 0;  // largest v with #(window < v) <= rank is the rank-th smallest value
+  for (int bit = 7; bit >= 0; --bit) {
+    const int cand = v | (1 << bit);
+    int cnt = 0;
+    for (int dy = -r; dy <= r; ++dy)
+      for (int dx = -r; dx <= r; ++dx) cnt += src[(long long)pcs_reflect_any(y + dy, H) * W + pcs_reflect_any(x + dx, W)] < cand;
+    if (cnt <= rank) v = cand;
+  }
+  out[t] = (uint8_t)v;
+}
+
 extern "C" {
 
 int pcs_dilate_bits(const uint32_t* in, uint32_t* out, const int32_t* runs, int n_runs, int invert_in, int border,
@@ -237,11 +290,15 @@ int pcs_majority_bits(const uint32_t* in, uint32_t* out, int size, int B, int H,
 int pcs_majority_bits_mask(const uint32_t* in, uint32_t* out, uint8_t* mask, int size, int B, int H, int W, void* stream) {
   PCS_REQUIRE(B >= 1 && H >= 1 && W >= 1, "empty batch or image");
   PCS_REQUIRE(size == 3 || size == 5 || size == 7, "median size must be 3, 5 or 7");
-  PCS_REQUIRE(H >= size && W >= size, "image smaller than the median window");
   PCS_REQUIRE(in != out, "median cannot run in place");
   int WW = pcs_words(W);
   unsigned g = pcs_blocks((long long)B * H * WW, MORPH_THREADS);
   cudaStream_t st = (cudaStream_t)stream;
+  if (H < size || W < size) {  // a side shorter than the window: general reflect fold
+    PCS_LAUNCH("k_majority_small", st, k_majority_small<<<pcs_blocks((long long)B * H * WW, 256), 256, 0, st>>>(in, out, size, B, H, W, WW));
+    if (mask) return pcs_unpack_bits(out, mask, B, H, W, stream);
+    return pcs_check_launch("majority");
+  }
   if (size == 3)
     PCS_LAUNCH("k_majority_bits", st, k_majority_bits<3><<<g, MORPH_THREADS, 0, st>>>(in, out, B, H, W, WW));
   else if (size == 5)
@@ -259,9 +316,12 @@ int pcs_majority_bits_mask(const uint32_t* in, uint32_t* out, uint8_t* mask, int
 int pcs_median_u8(const uint8_t* img, uint8_t* out, int size, int B, int H, int W, void* stream) {
   PCS_REQUIRE(B >= 1 && H >= 1 && W >= 1, "empty batch or image");
   PCS_REQUIRE(size == 3 || size == 5 || size == 7, "median size must be 3, 5 or 7");
-  PCS_REQUIRE(H >= size && W >= size, "image smaller than the median window");
   PCS_REQUIRE(img != out, "median cannot run in place");
   PCS_REQUIRE(B <= 65535, "batch above 65535");
+  if (H < size || W < size) {  // a side shorter than the window: general reflect fold
+    PCS_LAUNCH("k_median_small", (cudaStream_t)stream, k_median_small<<<pcs_blocks((long long)B * H * W, 256), 256, 0, (cudaStream_t)stream>>>(img, out, size, B, H, W));
+    return pcs_check_launch("median");
+  }
   dim3 grid((W + MED_TX - 1) / MED_TX, (H + MED_TY - 1) / MED_TY, B);
   dim3 block(MED_TX, MED_TY);
   cudaStream_t st = (cudaStream_t)stream;

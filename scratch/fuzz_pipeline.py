@@ -15,7 +15,7 @@ t0 = time.time(); n = 0; bad = 0
 while time.time() - t0 < budget:
     n += 1
     kind = rng.integers(0, 4)
-    Z = int(rng.integers(1, 4)); H = int(rng.integers(7, 300)); W = int(rng.integers(7, 700))
+    Z = int(rng.integers(1, 4)); H = int(rng.integers(1, 300)); W = int(rng.integers(1, 700))
     if kind == 0:
         st = synth.zstack_u16(Z, max(H, 8), max(W, 8), seed=int(rng.integers(1 << 30)))
     elif kind == 1:

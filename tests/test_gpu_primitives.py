@@ -148,7 +148,8 @@ def test_histogram_exact_when_counters_saturate(pcs):
 @pytest.mark.parametrize("size", [3, 5, 7])
 def test_median_u8(pcs, size):
     rng = np.random.default_rng(4)
-    for shape in [(7, 7), (16, 32), (33, 65), (130, 257)]:
+    # (1, 1) .. (3, 40): a side shorter than the window, where scipy's 'reflect' folds an index more than once
+    for shape in [(1, 1), (2, 5), (1, 70), (3, 40), (6, 2), (7, 7), (16, 32), (33, 65), (130, 257)]:
         for hi in (4, 256):
             a = rng.integers(0, hi, shape).astype(np.uint8)
             assert_same(pcs.ndimage.median_filter(a, size=size), ndi.median_filter(a, size=size), f"median {shape} hi={hi}")
