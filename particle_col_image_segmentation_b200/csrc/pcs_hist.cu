@@ -12,6 +12,8 @@
 // than 65536 pixels between flushes, which makes overflow impossible.  A flush
 // touches only non-zero bins, so global atomics drop from one per pixel to one
 // per distinct value per CTA.
+#include <cooperative_groups.h>
+
 #include "pcs_common.cuh"
 
 #include "pcs.h"
@@ -123,31 +125,54 @@ __device__ __forceinline__ OtsuBest otsu_better(OtsuBest a, OtsuBest b) {
   return a;
 }
 
-// one CTA per slice; thread t owns bins [64t, 64t+64)
-__global__ void __launch_bounds__(1024) k_otsu_u16(const uint32_t* __restrict__ hist, int32_t* __restrict__ thr,
-                                                   int32_t* __restrict__ minmax) {
-  __shared__ long long s_cnt[32], s_sum[32], s_tot[2];
+// One CLUSTER of four CTAs per slice: CTA r owns bins [16384 r, 16384 (r + 1)), thread t of it the 16 bins
+// from 16384 r + 16 t.  The CTAs exchange their totals and their best candidates through distributed shared
+// memory (two cluster barriers), so the fp64 evaluation of the 65536 candidate thresholds is spread over four
+// SMs instead of one -- with one CTA per slice a 64-slice batch used 64 of the 148 SMs and the kernel was
+// bound by the divisions of a single SM.
+#define OTSU_CTAS 4
+#define OTSU_BINS_PER_THREAD (65536 / OTSU_CTAS / 1024)
+
+struct OtsuCtaTotals {
+  long long cnt, sum;
+  int lo, hi;
+};
+
+__global__ void __cluster_dims__(OTSU_CTAS, 1, 1) __launch_bounds__(1024)
+    k_otsu_u16(const uint32_t* __restrict__ hist, int32_t* __restrict__ thr, int32_t* __restrict__ minmax) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned rank = cluster.block_rank();
+  __shared__ long long s_cnt[32], s_sum[32];
   __shared__ int s_lo[32], s_hi[32];
   __shared__ double s_var[32];
   __shared__ int s_idx[32];
+  __shared__ OtsuCtaTotals s_tot;  // this CTA's totals, read by the other CTAs of the cluster
+  __shared__ OtsuBest s_best;      // this CTA's best candidate, read by CTA 0
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const uint32_t* h = hist + (long long)blockIdx.x * 65536;
-  const uint4* h4 = reinterpret_cast<const uint4*>(h + tid * 64);
+  const int slice = blockIdx.x / OTSU_CTAS;
+  const int bin0 = (int)rank * (65536 / OTSU_CTAS) + tid * OTSU_BINS_PER_THREAD;
+  const uint32_t* h = hist + (long long)slice * 65536;
+  const uint4* h4 = reinterpret_cast<const uint4*>(h + bin0);
+  uint32_t c[OTSU_BINS_PER_THREAD];
+#pragma unroll
+  for (int i = 0; i < OTSU_BINS_PER_THREAD / 4; ++i) {
+    const uint4 q = __ldg(h4 + i);
+    c[4 * i] = q.x;
+    c[4 * i + 1] = q.y;
+    c[4 * i + 2] = q.z;
+    c[4 * i + 3] = q.w;
+  }
   long long cnt = 0, sum = 0;
   int lo = 65536, hi = -1;
-#pragma unroll 8
-  for (int i = 0; i < 16; ++i) {
-    uint4 q = __ldg(h4 + i);
-    const uint32_t c[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int v = tid * 64 + 4 * i + j;
-      cnt += c[j];
-      sum += (long long)c[j] * v;
-      if (c[j]) {
-        lo = min(lo, v);
-        hi = max(hi, v);
-      }
+  for (int j = 0; j < OTSU_BINS_PER_THREAD; ++j) {
+    const int v = bin0 + j;
+    cnt += c[j];
+    sum += (long long)c[j] * v;
+    if (c[j]) {
+      lo = min(lo, v);
+      hi = max(hi, v);
     }
   }
   // inclusive scans of (cnt, sum) across the warp, min / max of the occupied bins
@@ -186,37 +211,45 @@ __global__ void __launch_bounds__(1024) k_otsu_u16(const uint32_t* __restrict__ 
     s_cnt[lane] = ia - a;  // exclusive warp prefixes
     s_sum[lane] = is - s2;
     if (lane == 31) {
-      s_tot[0] = ia;
-      s_tot[1] = is;
-      s_lo[0] = mlo;
-      s_hi[0] = mhi;
+      s_tot.cnt = ia;
+      s_tot.sum = is;
+      s_tot.lo = mlo;
+      s_tot.hi = mhi;
     }
   }
-  __syncthreads();
-  const long long tot_cnt = s_tot[0], tot_sum = s_tot[1];
-  const int vmin = s_lo[0], vmax = s_hi[0];
-  long long run_cnt = s_cnt[wid] + (icnt - cnt);  // pixels strictly below this thread's first bin
-  long long run_sum = s_sum[wid] + (isum - sum);
-  OtsuBest best{0.0, -1};
-#pragma unroll 4
-  for (int i = 0; i < 16; ++i) {
-    uint4 q = __ldg(h4 + i);  // second read of the 256 KB histogram hits L2
-    const uint32_t c[4] = {q.x, q.y, q.z, q.w};
+  cluster.sync();  // every CTA's totals are in its shared memory
+  long long tot_cnt = 0, tot_sum = 0, before_cnt = 0, before_sum = 0;
+  int vmin = 65536, vmax = -1;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int v = tid * 64 + 4 * i + j;
-      run_cnt += c[j];
-      run_sum += (long long)c[j] * v;
-      // an empty bin leaves both classes as they were: its variance equals the previous bin's and can
-      // never be the FIRST maximum, so the (slow, fp64) evaluation is skipped for it
-      if (c[j] != 0u && v >= vmin && v < vmax) {
-        float w1 = (float)run_cnt, w2 = (float)(tot_cnt - run_cnt);  // exact: npix <= 2^24
-        double m1 = (double)run_sum / (double)w1;
-        double m2 = (double)(tot_sum - run_sum) / (double)w2;
-        double d = m1 - m2;
-        double var = __dmul_rn((double)__fmul_rn(w1, w2), __dmul_rn(d, d));
-        best = otsu_better(best, OtsuBest{var, v});
-      }
+  for (unsigned r = 0; r < OTSU_CTAS; ++r) {
+    const OtsuCtaTotals* t = cluster.map_shared_rank(&s_tot, r);
+    const long long tc = t->cnt, ts = t->sum;
+    tot_cnt += tc;
+    tot_sum += ts;
+    if (r < rank) {
+      before_cnt += tc;
+      before_sum += ts;
+    }
+    vmin = min(vmin, t->lo);
+    vmax = max(vmax, t->hi);
+  }
+  long long run_cnt = before_cnt + s_cnt[wid] + (icnt - cnt);  // pixels strictly below this thread's first bin
+  long long run_sum = before_sum + s_sum[wid] + (isum - sum);
+  OtsuBest best{0.0, -1};
+#pragma unroll
+  for (int j = 0; j < OTSU_BINS_PER_THREAD; ++j) {
+    const int v = bin0 + j;
+    run_cnt += c[j];
+    run_sum += (long long)c[j] * v;
+    // an empty bin leaves both classes as they were: its variance equals the previous bin's and can
+    // never be the FIRST maximum, so the (slow, fp64) evaluation is skipped for it
+    if (c[j] != 0u && v >= vmin && v < vmax) {
+      float w1 = (float)run_cnt, w2 = (float)(tot_cnt - run_cnt);  // exact: npix <= 2^24
+      double m1 = (double)run_sum / (double)w1;
+      double m2 = (double)(tot_sum - run_sum) / (double)w2;
+      double d = m1 - m2;
+      double var = __dmul_rn((double)__fmul_rn(w1, w2), __dmul_rn(d, d));
+      best = otsu_better(best, OtsuBest{var, v});
     }
   }
 #pragma unroll
@@ -236,14 +269,19 @@ __global__ void __launch_bounds__(1024) k_otsu_u16(const uint32_t* __restrict__ 
       OtsuBest other{__shfl_xor_sync(0xffffffffu, bb.var, o), __shfl_xor_sync(0xffffffffu, bb.idx, o)};
       bb = otsu_better(bb, other);
     }
-    if (lane == 0) {
-      thr[blockIdx.x] = (vmin == vmax || bb.idx < 0) ? vmin : bb.idx;  // single-valued image -> that value
-      if (minmax) {
-        minmax[2 * blockIdx.x] = vmin;
-        minmax[2 * blockIdx.x + 1] = vmax;
-      }
+    if (lane == 0) s_best = bb;
+  }
+  cluster.sync();  // every CTA's best candidate is in its shared memory
+  if (rank == 0 && tid == 0) {
+    OtsuBest bb = s_best;
+    for (unsigned r = 1; r < OTSU_CTAS; ++r) bb = otsu_better(bb, *cluster.map_shared_rank(&s_best, r));
+    thr[slice] = (vmin == vmax || bb.idx < 0) ? vmin : bb.idx;  // single-valued image -> that value
+    if (minmax) {
+      minmax[2 * slice] = vmin;
+      minmax[2 * slice + 1] = vmax;
     }
   }
+  cluster.sync();  // no CTA leaves while its shared memory may still be read
 }
 
 extern "C" {
@@ -277,7 +315,7 @@ int pcs_histogram_u16(const uint16_t* img, uint32_t* hist, int B, int H, int W, 
 int pcs_otsu_u16(const uint32_t* hist, int32_t* thr, int32_t* minmax, int B, int64_t npix, void* stream) {
   PCS_REQUIRE(B >= 1, "empty batch");
   PCS_REQUIRE(npix <= (1LL << 24), "Otsu parity needs at most 2^24 pixels per slice (float32 cumulative counts)");
-  PCS_LAUNCH("k_otsu_u16", (cudaStream_t)stream, k_otsu_u16<<<B, 1024, 0, (cudaStream_t)stream>>>(hist, thr, minmax));
+  PCS_LAUNCH("k_otsu_u16", (cudaStream_t)stream, k_otsu_u16<<<B * OTSU_CTAS, 1024, 0, (cudaStream_t)stream>>>(hist, thr, minmax));
   return pcs_check_launch("otsu");
 }
 
