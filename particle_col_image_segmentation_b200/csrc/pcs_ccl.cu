@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(CCL_TILE_THREADS) k_ccl_tile(P prov, int* __re
   }
   __syncthreads();
   const int n = nitems;
+  if (n == 0) return;  // empty tile (uniform): nothing to unite, nothing to publish
   // phase B, thread per NON-EMPTY word (all lanes busy): unions between runs of this tile
   for (int it = threadIdx.x; it < n; it += CCL_TILE_THREADS) {
     const int w = items[it], wr = w / TW, wc = w % TW;
@@ -674,6 +675,7 @@ __global__ void __launch_bounds__(PCS_CCL_THREADS)
   const long long t = b * H * WW + t32;
   const int k = t32 % WW, y = t32 / WW;
   P p = prov.slice(b);
+  const uint32_t ob = or_bits ? __ldg(or_bits + t) : 0u;  // requested beside the plane's own word, not after the parent walk
   uint32_t F, S;
   p.FS(y, k, F, S);
   uint32_t o = 0;
@@ -690,7 +692,7 @@ __global__ void __launch_bounds__(PCS_CCL_THREADS)
       if (marked == want_marked) o |= R;
     }
   }
-  if (or_bits) o |= or_bits[t];
+  o |= ob;
   out[t] = o;
   if (mask) pcs_store_mask_bytes(mask + (b * H + y) * (long long)prov.W, k, prov.W, o);  // fused uint8 output
 }
