@@ -64,17 +64,18 @@ NCU_TRAFFIC_BYTES_PER_VOXEL = {
 }
 
 
-def write_only_probe(dev):
-    """Best-of-5 fill of a 1 GiB buffer: the write-only ceiling of this GPU (the copy figure in
-    MEASURED_PEAKS.json counts read + write bytes; a store-only stream does not reach it)."""
+def write_only_probe(dev, lib):
+    """Best-of-5 fill of a 1 GiB buffer with the library's 128-bit store kernel: the store-only ceiling of this
+    GPU, next to the copy figure of MEASURED_PEAKS.json (which counts read + write bytes)."""
     import torch
 
-    x = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+    x = torch.empty(1 << 28, dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
     best = 1e9
     for _ in range(6):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        x.fill_(1)
+        lib.pcs_fill_u32(x.data_ptr(), 1, x.numel(), st)
         e1.record()
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
@@ -405,7 +406,7 @@ def run_b200(args):
         tpv = NCU_TRAFFIC_BYTES_PER_VOXEL.get(name)
         roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (tpv * per_launch_vox if tpv else None), "traffic_source": "ncu --set full, profiles/r1e_ncu_full_summary.txt (per voxel, scaled to this launch)" if tpv else None,
-                "write_only_gbs_live": write_only_probe(dev),
+                "write_only_gbs_live": write_only_probe(dev, lib),
                 "bytes_per_voxel": bpv, "avg_launch_ms": avg_ms, "launches": kcnt, "peak_source": peak_src, "kernel_time_share": shares,
                 "kernel_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
                 "timed": "per-kernel CUDA events on the launching stream over a second pass of the same K steps (eager launches)", "ms_per_step_with_events": ms_step_profiled}

@@ -65,6 +65,10 @@ int pcs_assign_where_u8(uint8_t* img, const uint32_t* bits, int value, int B, in
 /* out[i] = img[slice[i]][idx[i]]; dtype 0 u8, 2 i32, 5 i64 (tiff_analysis.py:845-852, :1041-1044) */
 int pcs_gather(const void* img, int dtype, const int64_t* slice, const int64_t* idx, int64_t* out, int64_t n, int64_t slice_elems, void* stream);
 
+/* dst[i] = value for n_words uint32 (multiple of 4, dst 16-byte aligned): grid-stride 128-bit stores; doubles as
+ * the store-only bandwidth probe of bench.py */
+int pcs_fill_u32(void* dst, uint32_t value, size_t n_words, void* stream);
+
 /* ---- K1: histogram + Otsu ------------------------------------------------------
  * skimage.filters.threshold_otsu on uint16 slices (north_star).
  * hist is uint32[B][65536]; thr receives the threshold, minmax (optional) 2 per slice. */

@@ -310,7 +310,23 @@ __global__ void __launch_bounds__(EDT_TW)
   // write the tile: background zeros and foreground distances in one coalesced sweep
   const long long obase = (b * H + (q << 5) + r0) * (long long)W + x0;
   if (dist) {
-    if (cols == EDT_TW && (W & 1) == 0 && ((((uintptr_t)dist) & 15) == 0)) {
+    if (cols == EDT_TW && (W & 3) == 0 && ((((uintptr_t)dist) & 31) == 0)) {
+      // four pixels per thread and one 256-bit streaming store: half the loop and address arithmetic of the
+      // 128-bit version, and a group of four background pixels (the common case) costs no table lookup
+      for (int i = tid; i < rows * (EDT_TW / 4); i += EDT_TW) {
+        const int r = i / (EDT_TW / 4), c = (i % (EDT_TW / 4)) * 4;
+        const uint2 pr = *reinterpret_cast<const uint2*>(&d2s[r][c]);
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+        if (pr.x | pr.y) {
+          v0 = g_edt_sqrt_lut[pr.x & 0xffffu];
+          v1 = g_edt_sqrt_lut[pr.x >> 16];
+          v2 = g_edt_sqrt_lut[pr.y & 0xffffu];
+          v3 = g_edt_sqrt_lut[pr.y >> 16];
+        }
+        double* dst = dist + obase + (long long)r * W + c;
+        asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(v0), "d"(v1), "d"(v2), "d"(v3) : "memory");
+      }
+    } else if (cols == EDT_TW && (W & 1) == 0 && ((((uintptr_t)dist) & 15) == 0)) {
       for (int i = tid; i < rows * (EDT_TW / 2); i += EDT_TW) {
         const int r = i / (EDT_TW / 2), c = (i % (EDT_TW / 2)) * 2;
         const uint32_t pr = *reinterpret_cast<const uint32_t*>(&d2s[r][c]);

@@ -262,6 +262,14 @@ static int launch_compare(const void* img, TT thr, const void* thr_dev, int cmp,
   return pcs_check_launch("compare");
 }
 
+// grid-stride fill with 128-bit stores: the store-only bandwidth probe bench.py reports next to the copy
+// figure (a plain kernel writes HBM at ~6.8 TB/s on B200; torch's uint8 fill_ reaches only ~3.9)
+__global__ void __launch_bounds__(256) k_fill128(uint4* __restrict__ p, uint32_t v, size_t n16) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n16; i += stride) p[i] = make_uint4(v, v, v, v);
+}
+
 extern "C" {
 
 int pcs_compare_u16(const uint16_t* img, int thr, const int32_t* thr_dev, int cmp, uint32_t* bits, uint8_t* mask, int B,
@@ -375,6 +383,16 @@ int pcs_gather(const void* img, int dtype, const int64_t* slice, const int64_t* 
     default: pcs_set_error("unsupported dtype for gather"); return PCS_ERR_UNSUPPORTED;
   }
   return pcs_check_launch("gather");
+}
+
+int pcs_fill_u32(void* dst, uint32_t value, size_t n_words, void* stream) {
+  PCS_REQUIRE(dst != nullptr && (n_words & 3) == 0 && ((((uintptr_t)dst) & 15) == 0), "fill needs a 16-byte aligned buffer of 4k words");
+  if (n_words == 0) return PCS_OK;
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  PCS_LAUNCH("k_fill128", (cudaStream_t)stream, k_fill128<<<sms * 16, 256, 0, (cudaStream_t)stream>>>((uint4*)dst, value, n_words / 4));
+  return pcs_check_launch("fill");
 }
 
 }  // extern "C"
