@@ -223,8 +223,29 @@ __global__ void __launch_bounds__(EDT_TW)
   {
     uint4* gz = reinterpret_cast<uint4*>(&g[0][0]);
     for (int i = tid; i < EDT_ER * EDT_TWH / 16; i += EDT_TW) gz[i] = make_uint4(0, 0, 0, 0);
-    uint4* dz = reinterpret_cast<uint4*>(&d2s[0][0]);
-    for (int i = tid; i < EDT_ER * EDT_TW / 8; i += EDT_TW) dz[i] = make_uint4(0, 0, 0, 0);
+    if (sq) {
+      uint4* dz = reinterpret_cast<uint4*>(&d2s[0][0]);
+      for (int i = tid; i < EDT_ER * EDT_TW / 8; i += EDT_TW) dz[i] = make_uint4(0, 0, 0, 0);
+    }
+  }
+  // The float64 output: the whole tile is cleared here with 256-bit stores (background pixels are at
+  // distance 0, and they are the majority); pass 2 then overwrites the foreground pixels one by one.  Both
+  // sets of stores come from this CTA with barriers in between, so they reach memory in order and merge in
+  // L2: DRAM still sees every line once.  Converting a shared tile of squared distances on the way out
+  // instead cost 30 % of the kernel's instructions (four table lookups per store, predicated for all).
+  const long long obase = (b * H + (q << 5) + r0) * (long long)W + x0;
+  if (dist) {
+    if (cols == EDT_TW && (W & 3) == 0 && ((((uintptr_t)dist) & 31) == 0)) {
+      for (int i = tid; i < rows * (EDT_TW / 4); i += EDT_TW) {
+        double* dst = dist + obase + (long long)(i / (EDT_TW / 4)) * W + (i % (EDT_TW / 4)) * 4;
+        asm volatile("st.global.v4.f64 [%0], {%1, %1, %1, %1};" ::"l"(dst), "d"(0.0) : "memory");
+      }
+    } else {
+      for (int i = tid; i < rows * EDT_TW; i += EDT_TW) {
+        const int r = i / EDT_TW, c = i % EDT_TW;
+        if (c < cols) dist[obase + (long long)r * W + c] = 0.0;
+      }
+    }
   }
   __syncthreads();
   // pass 1: vertical distances of the foreground pixels; the tile's own foreground pixels are also
@@ -303,47 +324,12 @@ __global__ void __launch_bounds__(EDT_TW)
       const uint32_t g1 = g[r][c - (int)dd], g2 = g[r][c + (int)dd];
       best = min(best, min(d2d + g1 * g1, d2d + g2 * g2));  // clamped columns (255^2) never win
     }
-    d2s[r][c - EDT_HALO] = (uint16_t)best;
+    if (dist) dist[obase + (long long)r * W + (c - EDT_HALO)] = g_edt_sqrt_lut[best];
+    if (sq) d2s[r][c - EDT_HALO] = (uint16_t)best;
     if (thr_bits && (int)best <= thr_sq) atomicOr(&tb[r][(c - EDT_HALO) >> 5], 1u << ((c - EDT_HALO) & 31));
   }
   __syncthreads();
-  // write the tile: background zeros and foreground distances in one coalesced sweep
-  const long long obase = (b * H + (q << 5) + r0) * (long long)W + x0;
-  if (dist) {
-    if (cols == EDT_TW && (W & 3) == 0 && ((((uintptr_t)dist) & 31) == 0)) {
-      // four pixels per thread and one 256-bit streaming store: half the loop and address arithmetic of the
-      // 128-bit version, and a group of four background pixels (the common case) costs no table lookup
-      for (int i = tid; i < rows * (EDT_TW / 4); i += EDT_TW) {
-        const int r = i / (EDT_TW / 4), c = (i % (EDT_TW / 4)) * 4;
-        const uint2 pr = *reinterpret_cast<const uint2*>(&d2s[r][c]);
-        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-        if (pr.x | pr.y) {
-          v0 = g_edt_sqrt_lut[pr.x & 0xffffu];
-          v1 = g_edt_sqrt_lut[pr.x >> 16];
-          v2 = g_edt_sqrt_lut[pr.y & 0xffffu];
-          v3 = g_edt_sqrt_lut[pr.y >> 16];
-        }
-        double* dst = dist + obase + (long long)r * W + c;
-        asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(v0), "d"(v1), "d"(v2), "d"(v3) : "memory");
-      }
-    } else if (cols == EDT_TW && (W & 1) == 0 && ((((uintptr_t)dist) & 15) == 0)) {
-      for (int i = tid; i < rows * (EDT_TW / 2); i += EDT_TW) {
-        const int r = i / (EDT_TW / 2), c = (i % (EDT_TW / 2)) * 2;
-        const uint32_t pr = *reinterpret_cast<const uint32_t*>(&d2s[r][c]);
-        double2 v = make_double2(0.0, 0.0);
-        if (pr) {
-          v.x = g_edt_sqrt_lut[pr & 0xffffu];
-          v.y = g_edt_sqrt_lut[pr >> 16];
-        }
-        __stcs(reinterpret_cast<double2*>(dist + obase + (long long)r * W + c), v);
-      }
-    } else {
-      for (int i = tid; i < rows * EDT_TW; i += EDT_TW) {
-        const int r = i / EDT_TW, c = i % EDT_TW;
-        if (c < cols) dist[obase + (long long)r * W + c] = g_edt_sqrt_lut[d2s[r][c]];
-      }
-    }
-  }
+  // the squared-distance output (when asked for) leaves through the shared tile in one coalesced sweep
   if (sq) {
     if (cols == EDT_TW && (W & 3) == 0 && ((((uintptr_t)sq) & 15) == 0)) {
       for (int i = tid; i < rows * (EDT_TW / 4); i += EDT_TW) {
