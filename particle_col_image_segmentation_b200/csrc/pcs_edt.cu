@@ -192,7 +192,9 @@ __global__ void __launch_bounds__(EDT_TW)
   __shared__ __align__(16) uint8_t g[EDT_ER][EDT_TWH];
   __shared__ __align__(16) uint16_t d2s[EDT_ER][EDT_TW];
   __shared__ uint32_t tb[EDT_ER][EDT_TW / 32];
-  __shared__ unsigned short items[EDT_ER * EDT_TW];  // (row << 9 | tile column) of the tile's foreground pixels
+  __shared__ unsigned short items[EDT_ER * EDT_TWH];  // (row << 9 | column) of the foreground pixels of tile + halo
+  __shared__ uint32_t zcol[EDT_TWH];                   // background rows of every column (vertical word, inverted)
+  __shared__ unsigned short cucol[EDT_TWH], cdcol[EDT_TWH];  // carries beyond the band, per column
   __shared__ int nitems;
   const int tid = threadIdx.x;
   if (tid == 0) nitems = 0;
@@ -248,34 +250,25 @@ __global__ void __launch_bounds__(EDT_TW)
     }
   }
   __syncthreads();
-  // pass 1: vertical distances of the foreground pixels; the tile's own foreground pixels are also
-  // appended to a work list so that pass 2 spreads them evenly over the CTA (a thread per pixel,
-  // not a thread per column: columns through a particle would serialise ~20 searches)
+  // pass 1a, thread per column: list the foreground pixels of tile + halo (warp-level exclusive scan of the
+  // per-column counts) and park the column's word and carries in shared memory
 #pragma unroll
   for (int slot = 0; slot < 2; ++slot) {
     if (slot == 1 && tid >= 2 * EDT_HALO) break;
     const int col = tid + slot * EDT_TW;
-    const int x = slot ? xb : xa;
     const uint32_t fw = slot ? fb : fa;
     uint32_t f = (fw >> r0) & ((EDT_ER == 32) ? 0xffffffffu : ((1u << EDT_ER) - 1u));  // this CTA's rows of the column
+    if (rows < EDT_ER) f &= (1u << rows) - 1u;
     if (slot ? inb : ina) {
-      if (f) {
-        const uint32_t z = ~fw, cu = slot ? cub : cua, cd = slot ? cdb : cda;
-        uint32_t ff = f;
-        while (ff) {
-          const int r = __ffs(ff) - 1;
-          ff &= ff - 1;
-          g[r][col] = (uint8_t)min(edt_vdist(z, r0 + r, cu, cd), EDT_GCLAMP);
-        }
-      }
+      zcol[col] = ~fw;
+      cucol[col] = (unsigned short)(slot ? cub : cua);
+      cdcol[col] = (unsigned short)(slot ? cdb : cda);
     } else {
+      f = 0;
 #pragma unroll 8
       for (int r = 0; r < EDT_ER; ++r) g[r][col] = (uint8_t)EDT_GCLAMP;  // outside the image: no site
     }
-    // work items of interior columns (warp-level exclusive scan of the per-column counts)
-    const bool interior = col >= EDT_HALO && col < EDT_HALO + EDT_TW && x < W;
-    if (rows < EDT_ER) f &= (1u << rows) - 1u;
-    const int cnt = interior ? __popc(f) : 0;
+    const int cnt = __popc(f);
     const unsigned act = __activemask();
     int incl = cnt;
 #pragma unroll
@@ -299,6 +292,15 @@ __global__ void __launch_bounds__(EDT_TW)
     }
   }
   __syncthreads();
+  // pass 1b, thread per listed pixel: its vertical distance.  Done per pixel, not per column, because the
+  // foreground comes in blobs: a thread per column left most warps idle behind the few that cross a blob.
+  const int n = nitems;
+  for (int it = tid; it < n; it += EDT_TW) {
+    const int item = items[it];
+    const int r = item >> 9, c = item & 511;
+    g[r][c] = (uint8_t)min(edt_vdist(zcol[c], r0 + r, cucol[c], cdcol[c]), EDT_GCLAMP);
+  }
+  __syncthreads();
   if (thr_bits) {
     // background pixels are at distance 0: start every row word from them (warp w owns word w)
     const int x = x0 + tid;
@@ -308,11 +310,11 @@ __global__ void __launch_bounds__(EDT_TW)
     }
     __syncthreads();
   }
-  // pass 2: thread per foreground pixel
-  const int n = nitems;
+  // pass 2: thread per foreground pixel of the tile proper (halo pixels only lend their g)
   for (int it = tid; it < n; it += EDT_TW) {
     const int item = items[it];
     const int r = item >> 9, c = item & 511;
+    if (c < EDT_HALO || c >= EDT_HALO + EDT_TW) continue;
     const uint32_t gx = g[r][c];
     if (gx > EDT_DMAX) {
       row_far[b * H + (q << 5) + r0 + r] = 1;  // solved by k_edt_far, which rewrites the whole row
