@@ -55,12 +55,12 @@ KERNEL_BYTES_PER_VOXEL = {
 
 # DRAM traffic per voxel of the dominant kernels from the `ncu --set full` capture of profiles/prof_step.py
 # (16 slices of 2048^2 per launch; dram__bytes_read.sum + dram__bytes_write.sum over 67.1 Mvoxel), see
-# profiles/r1j_ncu_full_summary.txt.  Below the algorithmic figure where part of the output is still in L2
+# profiles/r1k_ncu_full_summary.txt.  Below the algorithmic figure where part of the output is still in L2
 # when the kernel ends.
 NCU_TRAFFIC_BYTES_PER_VOXEL = {
-    "k_edt_near": (16.81 + 478.38) / 67.109,
-    "k_hist_u16": (136.01 + 5.31) / 67.109,
-    "k_ccl_relabel": (60.45 + 214.15) / 67.109,
+    "k_edt_near": (16.81 + 480.48) / 67.109,
+    "k_hist_u16": (136.02 + 4.80) / 67.109,
+    "k_ccl_relabel": (60.45 + 209.11) / 67.109,
 }
 
 
@@ -405,7 +405,7 @@ def run_b200(args):
         achieved = bpv * per_launch_vox / (avg_ms * 1e-3) / 1e9
         tpv = NCU_TRAFFIC_BYTES_PER_VOXEL.get(name)
         roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": (tpv * per_launch_vox if tpv else None), "traffic_source": "ncu --set full, profiles/r1j_ncu_full_summary.txt (per voxel, scaled to this launch)" if tpv else None,
+                "traffic": (tpv * per_launch_vox if tpv else None), "traffic_source": "ncu --set full, profiles/r1k_ncu_full_summary.txt (per voxel, scaled to this launch)" if tpv else None,
                 "write_only_gbs_live": write_only_probe(dev, lib),
                 "bytes_per_voxel": bpv, "avg_launch_ms": avg_ms, "launches": kcnt, "peak_source": peak_src, "kernel_time_share": shares,
                 "kernel_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
