@@ -104,18 +104,20 @@ __global__ void __launch_bounds__(CCL_TILE_THREADS) k_ccl_tile(P prov, int* __re
   const long long b = blockIdx.z;
   P p = prov.slice(b);
   if (threadIdx.x == 0) nitems = 0;
-  __syncthreads();
   // phase A, thread per word: stage the tile, give every run its own slot, list the non-empty words.
   // The words of all of a thread's iterations are requested first (one memory round trip, not one each).
   constexpr int NPT = (NWORDS + CCL_TILE_THREADS - 1) / CCL_TILE_THREADS;
   uint32_t Fpre[NPT], Spre[NPT];
+  uint32_t any = 0u;
 #pragma unroll
   for (int i = 0; i < NPT; ++i) {
     const int w = threadIdx.x + i * CCL_TILE_THREADS;
     const int k = k0 + w % TW, y = y0 + w / TW;
     Fpre[i] = Spre[i] = 0u;
     if (w < NWORDS && y < H && k < WW) p.FS(y, k, Fpre[i], Spre[i]);
+    any |= Fpre[i];
   }
+  if (!__syncthreads_or(any != 0u)) return;  // empty tile: the common case on sparse planes (hole candidates)
 #pragma unroll
   for (int i = 0; i < NPT; ++i) {
     const int w = threadIdx.x + i * CCL_TILE_THREADS;
