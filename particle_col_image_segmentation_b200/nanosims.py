@@ -17,7 +17,7 @@ here unchanged.
 import numpy as np
 import torch
 
-from . import _io, ops
+from . import _io, _lib, ops
 
 PLANES_7 = ("12C", "13C", "14N12C", "15N12C", "16O", "17O", "18O")
 ACTIVITIES_7 = (("13C", (1, (1, 0))), ("15N", (3, (2, 3))), ("17O", (5, (6, 5, 4))), ("18O", (6, (6, 5, 4))))
@@ -108,14 +108,8 @@ def imgaussfilt(a, sigma):
     t = _f64_image(a)
     out, tmp = torch.empty_like(t), torch.empty_like(t)
     H, W = t.shape
-    _lib_call("pcs_gauss_f64", ops._p(t), ops._p(out), ops._p(tmp), float(sigma), 1, int(H), int(W), ops._stream())
+    _lib.call("pcs_gauss_f64", ops._p(t), ops._p(out), ops._p(tmp), float(sigma), 1, int(H), int(W), ops._stream())
     return _io.back(out, _io.is_numpy(a))
-
-
-def _lib_call(name, *args):
-    from . import _lib
-
-    _lib.call(name, *args)
 
 
 def scaled_uint8(num, dens=()):
@@ -128,9 +122,9 @@ def scaled_uint8(num, dens=()):
     ratio = torch.empty_like(n)
     maxv = torch.empty(1, dtype=torch.float64, device=n.device)
     p = [ops._p(d) for d in ds] + [0] * (3 - len(ds))
-    _lib_call("pcs_ratio_f64", ops._p(n), p[0], p[1], p[2], ops._p(ratio), ops._p(maxv), int(n.numel()), ops._stream())
+    _lib.call("pcs_ratio_f64", ops._p(n), p[0], p[1], p[2], ops._p(ratio), ops._p(maxv), int(n.numel()), ops._stream())
     out = torch.empty(n.shape, dtype=torch.uint8, device=n.device)
-    _lib_call("pcs_scale_u8_f64", ops._p(ratio), ops._p(maxv), ops._p(out), int(n.numel()), ops._stream())
+    _lib.call("pcs_scale_u8_f64", ops._p(ratio), ops._p(maxv), ops._p(out), int(n.numel()), ops._stream())
     return _io.back(out, _io.is_numpy(num))
 
 
