@@ -370,10 +370,22 @@ def run_b200(args):
 
     # end to end through the public API with host buffers (pinned), copies inside the timed region
     e2e = None
-    if not args.no_e2e:
-        host_in = torch.empty((Z, S, S), dtype=torch.uint16).pin_memory()
-        host_in.copy_(stack)
-        host_out = split_zstack.alloc_host_outputs(Z, S, S)
+    e2e_ok = not args.no_e2e
+    if e2e_ok:
+        # 4.3 GB of pinned host memory per rank: if any rank cannot get it, every rank skips the e2e leg
+        # (a lone failing rank would leave the others waiting in the barrier)
+        try:
+            host_in = torch.empty((Z, S, S), dtype=torch.uint16).pin_memory()
+            host_in.copy_(stack)
+            host_out = split_zstack.alloc_host_outputs(Z, S, S)
+        except RuntimeError as e:  # noqa: BLE001
+            sys.stderr.write(f"bench: rank {rank}: no pinned host buffers ({str(e)[:120]}); e2e skipped\n")
+            e2e_ok = False
+        if world > 1:
+            flag = torch.tensor([1 if e2e_ok else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            e2e_ok = bool(flag.item())
+    if e2e_ok:
         split_zstack.segment_zstack_pinned(host_in, host_out, chunk=args.e2e_chunk)  # warm-up
         barrier()
         t0 = time.perf_counter()
