@@ -179,3 +179,20 @@ def test_segment_tif_matches_oracle(tmp_path):
     want = opipe.segment_zstack(planes)
     assert np.array_equal(out["labels"].numpy(), want["labels"]) and np.array_equal(out["edt"].numpy(), want["edt"])
     assert np.array_equal(out["refined"].numpy().astype(bool), want["refined"]) and np.array_equal(out["table"].numpy(), want["table"])
+
+
+def test_read_stack_pinned_without_a_gpu(tmp_path):
+    """The pinned reader degrades to pageable memory when no CUDA device is present; the pixels are the same."""
+    import torch
+
+    rng = np.random.default_rng(6)
+    stack = rng.integers(0, 65535, (2, 3, 9, 14), dtype=np.uint16)
+    p = str(tmp_path / "p.tif")
+    tiff_io.write_stack(p, stack)
+    t = tiff_io.read_stack_pinned(p)
+    assert t.dtype == torch.uint16 and tuple(t.shape) == stack.shape and np.array_equal(t.numpy(), stack)
+    assert t.is_pinned() == torch.cuda.is_available()
+    big = str(tmp_path / "be.tif")
+    open(big, "wb").write(_hand_tiff([stack[0, 0]], bo=">"))
+    with pytest.raises(tiff_io.TiffError, match="big-endian"):
+        tiff_io.read_stack_pinned(big)
