@@ -25,20 +25,24 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(HERE, "..", "include", "pcs.h")]
+    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.inc")) + [os.path.join(HERE, "..", "include", "pcs.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, variant=None, extra_flags=()):
+    """``variant`` / ``extra_flags``: an A/B build with extra ``-D`` flags into ``libpcs_<variant>.so`` (load it with
+    ``PCS_LIB_PATH``); tuning only, the product is the plain ``libpcs.so``."""
+    lib = LIB if not variant else os.path.join(HERE, f"libpcs_{variant}.so")
+    if not variant and not force and not needs_build():
         return LIB
     objs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    bdir = os.path.join(HERE, "build" if not variant else f"build_{variant}")
+    os.makedirs(bdir, exist_ok=True)
     procs = []
     for src in sources():
-        obj = os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(bdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [NVCC, *FLAGS, "-c", src, "-o", obj]
+        cmd = [NVCC, *FLAGS, *extra_flags, "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -50,9 +54,10 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed building libpcs.so")
-    subprocess.check_call([NVCC, "-shared", "-o", LIB, *objs, "-lcudart"])
-    return LIB
+    subprocess.check_call([NVCC, "-shared", "-o", lib, *objs, "-lcudart"])
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    variant = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")), None)
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=variant, extra_flags=[a for a in sys.argv[1:] if a.startswith("-D")]))

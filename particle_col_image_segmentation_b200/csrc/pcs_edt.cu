@@ -166,14 +166,14 @@ __device__ __forceinline__ uint32_t edt_vdist(uint32_t z, int r, uint32_t cu, ui
 }
 
 // sqrt of the squared distances the near phase can produce (<= EDT_DMAX^2): one L1-resident load
-// instead of a 45-instruction fp64 sqrt per foreground pixel; filled on the device with the same
-// IEEE sqrt the far phase uses, so both phases round identically.
+// instead of a 45-instruction fp64 sqrt per foreground pixel.  The table is a compile-time constant
+// (exact hexadecimal literals of the correctly rounded square roots, identical to what the far phase's
+// sqrt() returns), so no initialisation kernel exists that a first call on another stream, inside a
+// graph capture or from another thread could race with.
 #define EDT_LUT_N (EDT_DMAX * EDT_DMAX + 1)
-__device__ double g_edt_sqrt_lut[EDT_LUT_N];
-__global__ void k_edt_lut_init() {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < (int)EDT_LUT_N) g_edt_sqrt_lut[i] = sqrt((double)i);
-}
+__device__ const double g_edt_sqrt_lut[EDT_LUT_N] = {
+#include "pcs_edt_sqrt_lut.inc"
+};
 
 // Phase 1: CTA per (column tile, band, slice).  Every pixel whose vertical distance is at most
 // EDT_DMAX is final after an outward search inside the tile + halo; the others flag their row.
@@ -443,15 +443,6 @@ int pcs_edt_bits(const uint32_t* bits, int invert, int B, int H, int W, double* 
              k_edt_transpose<<<pcs_blocks((long long)B * NB * ((WW + 3) / 4) * 32, 256), 256, 0, st>>>(bits, invert, vw, B, H, W, WW, NB));
   dim3 gc((W + 127) / 128, B, 2);
   PCS_LAUNCH("k_edt_carry", st, k_edt_carry<<<gc, 128, 0, st>>>(vw, up, dn, W, Wp, NB));
-  {
-    static bool lut_ready[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !lut_ready[dev]) {
-      PCS_LAUNCH("k_edt_lut_init", st, k_edt_lut_init<<<(EDT_LUT_N + 255) / 256, 256, 0, st>>>());
-      lut_ready[dev] = true;
-    }
-  }
   dim3 gn((W + EDT_TW - 1) / EDT_TW, NB * (32 / EDT_ER), B);
   PCS_LAUNCH("k_edt_near", st,
              k_edt_near<<<gn, EDT_TW, 0, st>>>(vw, up, dn, dist, sq, thr_bits, thr_sq, row_far, H, W, WW, NB));

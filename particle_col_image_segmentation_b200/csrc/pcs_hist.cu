@@ -18,8 +18,15 @@
 
 #include "pcs.h"
 
+#ifndef HIST_THREADS
 #define HIST_THREADS 1024
-#define HIST_VEC_PER_THREAD 7                                  // uint4 loads (8 px each)
+#endif
+#ifndef HIST_VEC_PER_THREAD
+#define HIST_VEC_PER_THREAD 7  // uint4 loads (8 px each)
+#endif
+#ifndef HIST_MINBLOCKS
+#define HIST_MINBLOCKS 1
+#endif
 #define HIST_PIX_PER_BLOCK (HIST_THREADS * HIST_VEC_PER_THREAD * 8)  // 57344 < 65536
 #define HIST_SMEM_BYTES (32768 * 4)
 
@@ -33,56 +40,73 @@ __device__ __forceinline__ void hist_count8(uint32_t* sh, const uint4& q) {
   }
 }
 
-// CTA = `tiles` consecutive tiles of HIST_PIX_PER_BLOCK pixels of one slice.
-//  * The pixels of tile t + 1 are requested while tile t is being counted: as soon as a vector has been
-//    counted its registers receive the same vector of the next tile, so the HBM round trip hides behind the
+// PERSISTENT kernel: at most one CTA per SM, CTA c walks a contiguous range of the flattened (slice, tile) space
+// (tile = HIST_PIX_PER_BLOCK consecutive pixels of one slice).
+//  * The pixels of the next tile are requested while the current one is being counted: as soon as a vector has
+//    been counted its registers receive the same vector of the next tile, so the HBM round trip hides behind the
 //    remaining atomics (the first version loaded and counted vector by vector and mostly waited for loads).
 //  * The packed counters are flushed only when one of them could overflow during the next tile, i.e. when
 //    some counter has reached 65536 - HIST_PIX_PER_BLOCK = 8192 (a one-instruction test per word while
-//    scanning shared memory), and at the end.  On micrographs the fullest bin takes < 1 % of the pixels, so a
-//    CTA flushes once instead of once per tile; an image of one value still flushes every tile and stays exact.
-__global__ void __launch_bounds__(HIST_THREADS, 1)
-    k_hist_u16(const uint16_t* __restrict__ img, uint32_t* __restrict__ hist, long long npix, int tiles) {
+//    scanning shared memory), when the walk crosses into another slice, and at the end.  On micrographs the
+//    fullest bin takes < 1 % of the pixels, so a CTA flushes about once per slice it touches; an image of one
+//    value still flushes every tile and stays exact.
+//  * Why persistent: the grid never exceeds the SM count, so every CTA is dispatched at once and the block
+//    scheduler moves on to kernels of OTHER streams, which fit beside this one (1024 threads and 99 KB of shared
+//    memory stay free per SM).  With more CTAs than SMs the pending ones kept other streams' kernels out and the
+//    atomics-bound histogram never overlapped the bandwidth-bound kernels of the neighbouring chunk
+//    (scratch/probe_r2a.py: 0.274 ms beside a 1 GiB fill vs 0.288 ms one after the other).
+__global__ void __launch_bounds__(HIST_THREADS, HIST_MINBLOCKS)
+    k_hist_u16(const uint16_t* __restrict__ img, uint32_t* __restrict__ hist, long long npix, int ntiles, long long total_tiles) {
   extern __shared__ uint32_t sh[];  // 32768 words, two 16-bit counters each
   const int tid = threadIdx.x;
   uint4* sh4 = reinterpret_cast<uint4*>(sh);
 #pragma unroll
   for (int i = 0; i < 32768 / 4 / HIST_THREADS; ++i) sh4[tid + i * HIST_THREADS] = make_uint4(0, 0, 0, 0);
-  const long long b = blockIdx.y;
-  const uint16_t* src = img + b * npix;
-  uint32_t* g = hist + b * 65536;
-  const bool aligned = ((((uintptr_t)src) & 15) == 0);
-  const long long start0 = (long long)blockIdx.x * tiles * HIST_PIX_PER_BLOCK;
-  auto full_tile = [&](long long start) { return aligned && start + HIST_PIX_PER_BLOCK <= npix; };
+  // tiles [g0, g1) of the flattened space belong to this CTA
+  const long long g0 = total_tiles * blockIdx.x / gridDim.x, g1 = total_tiles * (blockIdx.x + 1) / gridDim.x;
+  auto tile_src = [&](long long g, long long& start) {
+    const long long b = g / ntiles;
+    start = (g - b * ntiles) * HIST_PIX_PER_BLOCK;
+    return img + b * npix;
+  };
+  auto full_tile = [&](const uint16_t* src, long long start) {
+    return ((((uintptr_t)src) & 15) == 0) && start + HIST_PIX_PER_BLOCK <= npix;
+  };
   uint4 cur[HIST_VEC_PER_THREAD];
-  if (start0 < npix && full_tile(start0)) {
-    const uint4* s4 = reinterpret_cast<const uint4*>(src + start0) + tid;
+  if (g0 < g1) {
+    long long start;
+    const uint16_t* src = tile_src(g0, start);
+    if (full_tile(src, start)) {
+      const uint4* s4 = reinterpret_cast<const uint4*>(src + start) + tid;
 #pragma unroll
-    for (int v = 0; v < HIST_VEC_PER_THREAD; ++v) cur[v] = __ldg(s4 + v * HIST_THREADS);
+      for (int v = 0; v < HIST_VEC_PER_THREAD; ++v) cur[v] = __ldg(s4 + v * HIST_THREADS);
+    }
   }
   __syncthreads();
-  for (int t = 0; t < tiles; ++t) {
-    const long long start = start0 + (long long)t * HIST_PIX_PER_BLOCK;
-    if (start >= npix) break;
-    const long long next = start + HIST_PIX_PER_BLOCK;
-    const bool have_next = t + 1 < tiles && next < npix && full_tile(next);
-    if (full_tile(start)) {
-      const uint4* n4 = reinterpret_cast<const uint4*>(src + next) + tid;
+  for (long long g = g0; g < g1; ++g) {
+    long long start, nstart = 0;
+    const uint16_t* src = tile_src(g, start);
+    const uint16_t* nsrc = src;
+    const bool more = g + 1 < g1;
+    if (more) nsrc = tile_src(g + 1, nstart);
+    const bool have_next = more && full_tile(nsrc, nstart);
+    if (full_tile(src, start)) {
+      const uint4* n4 = reinterpret_cast<const uint4*>(nsrc + nstart) + tid;
 #pragma unroll
       for (int v = 0; v < HIST_VEC_PER_THREAD; ++v) {
         hist_count8(sh, cur[v]);
         if (have_next) cur[v] = __ldg(n4 + v * HIST_THREADS);
       }
     } else {  // ragged tail or unaligned slice
-      const long long end = min(npix, next);
+      const long long end = min(npix, start + HIST_PIX_PER_BLOCK);
       for (long long i = start + tid; i < end; i += HIST_THREADS) {
         const uint32_t a = src[i];
         atomicAdd(&sh[a >> 1], 1u << ((a & 1u) << 4));
       }
     }
     __syncthreads();
-    const bool last = t + 1 >= tiles || next >= npix;
-    int hot = 0;  // some counter at 8192 or above: the next tile could overflow it
+    const bool last = !more || nsrc != src;  // end of this CTA's range or of the slice
+    int hot = 0;                             // some counter at 8192 or above: the next tile could overflow it
     if (!last) {
 #pragma unroll
       for (int i = 0; i < 32768 / 4 / HIST_THREADS; ++i) {
@@ -91,7 +115,8 @@ __global__ void __launch_bounds__(HIST_THREADS, 1)
       }
     }
     if (!__syncthreads_or(hot | (int)last)) continue;
-    // flush the non-zero counters and clear them
+    // flush the non-zero counters into the slice's histogram and clear them
+    uint32_t* gh = hist + (g / ntiles) * 65536;
 #pragma unroll
     for (int i = 0; i < 32768 / 4 / HIST_THREADS; ++i) {
       const int idx = tid + i * HIST_THREADS;
@@ -103,8 +128,8 @@ __global__ void __launch_bounds__(HIST_THREADS, 1)
           if (w[j]) {
             const int bin = (idx * 4 + j) * 2;
             const uint32_t lo = w[j] & 0xffffu, hi = w[j] >> 16;
-            if (lo) atomicAdd(g + bin, lo);
-            if (hi) atomicAdd(g + bin + 1, hi);
+            if (lo) atomicAdd(gh + bin, lo);
+            if (hi) atomicAdd(gh + bin + 1, hi);
           }
         }
         sh4[idx] = make_uint4(0, 0, 0, 0);
@@ -295,20 +320,17 @@ int pcs_histogram_u16(const uint16_t* img, uint32_t* hist, int B, int H, int W, 
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(hist, 0, pcs_histogram_bytes(B), st);
   long long npix = (long long)H * W;
-  // a few consecutive tiles per CTA so that the next tile's loads overlap the current tile's atomics and
-  // flush, and one flush serves several tiles; about four CTAs per SM overall keeps the tail short
+  // one persistent CTA per SM (or fewer when there are fewer tiles), each walking a contiguous tile range
   const long long ntiles = (npix + HIST_PIX_PER_BLOCK - 1) / HIST_PIX_PER_BLOCK;
+  const long long total = ntiles * B;
   int sms = 148;
   {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  long long per = (ntiles * B + 4LL * sms - 1) / (4LL * sms);
-  if (per < 1) per = 1;
-  if (per > ntiles) per = ntiles;
-  dim3 grid((unsigned)((ntiles + per - 1) / per), B);
-  PCS_LAUNCH("k_hist_u16", st, k_hist_u16<<<grid, HIST_THREADS, HIST_SMEM_BYTES, st>>>(img, hist, npix, (int)per));
+  const unsigned grid = (unsigned)(total < sms ? total : sms);
+  PCS_LAUNCH("k_hist_u16", st, k_hist_u16<<<grid, HIST_THREADS, HIST_SMEM_BYTES, st>>>(img, hist, npix, (int)ntiles, total));
   return pcs_check_launch("histogram");
 }
 
