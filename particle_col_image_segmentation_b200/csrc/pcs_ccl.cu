@@ -215,26 +215,19 @@ __global__ void __launch_bounds__(CCL_TILE_THREADS) k_ccl_tile(P prov, int* __re
     }
   }
   __syncthreads();
-  // phase C, thread per non-empty word: every node points at the global index of its tile-local root
-  const int Wp = WW << 5;
-  int* par = parent + b * (long long)H * Wp;
+  // phase C, thread per non-empty word: every node points at the global id of its tile-local root
+  // (tile slot = word-in-tile * SPW + ordinal, global id = word * SPW + ordinal: only the word changes)
+  const int NW = H * WW;
+  int* par = parent + b * ((long long)NW << LSPW);
   for (int it = threadIdx.x; it < n; it += CCL_TILE_THREADS) {
     const int w = items[it], wr = w / TW, wc = w % TW;
     const int sbase = w << LSPW;
-    const int gbase = (y0 + wr) * Wp + ((k0 + wc) << 5);
-    uint32_t S = ssm[w];
-    int j = 0;
-    while (S) {
-      int s = __ffs(S) - 1;
-      S &= S - 1;
-      int root = pcs_lfind(sp, sbase + j);
-      int rw = root >> LSPW, rj = root & (SPW - 1);  // word of the root inside the tile, run ordinal
-      // start bit of the rj-th run of that word: clear the rj lowest start bits, take the next
-      uint32_t rsb = ssm[rw];
-      for (int q = 0; q < rj; ++q) rsb &= rsb - 1;
-      int rs = __ffs(rsb) - 1;
-      par[gbase + s] = (y0 + rw / TW) * Wp + ((k0 + rw % TW) << 5) + rs;
-      ++j;
+    const int gw = (y0 + wr) * WW + k0 + wc;
+    const int nruns = __popc(ssm[w]);
+    for (int j = 0; j < nruns; ++j) {
+      const int root = pcs_lfind(sp, sbase + j);
+      const int rw = root >> LSPW, rj = root & (SPW - 1);  // word of the root inside the tile, run ordinal
+      par[j * NW + gw] = pcs_node<LSPW>((y0 + rw / TW) * WW + k0 + rw % TW, rj);
     }
   }
 }
@@ -269,17 +262,17 @@ __global__ void __launch_bounds__(PCS_CCL_THREADS) k_ccl_merge_edges(P prov, int
   if (!F0) return;
   PcsConnWords c;
   p.conn(y, k, c);
-  const int Wp = WW << 5;
-  int* par = parent + b * (long long)H * Wp;
-  const int base = y * Wp + (k << 5);
+  constexpr int LSPW = PcsNodes<P>::LOG_SPW;
+  const int NW = H * WW;
+  int* par = parent + b * ((long long)NW << LSPW);
+  const int gw = y * WW + k;
   if (c.J && left) {
     uint32_t Sl = p.Sword(y, k - 1);
-    pcs_uf_union(par, base, base - 32 + (31 - __clz(Sl)));
+    pcs_uf_union<LSPW>(par, NW, pcs_node<LSPW>(gw, 0), pcs_node<LSPW>(gw - 1, __popc(Sl) - 1));  // last run of the word to the left
   }
   if (y == 0 || !(c.U | c.UL | c.UR)) return;
   uint32_t S = c.S;
-  const int abase = (y - 1) * Wp + (k << 5);
-  while (S) {
+  for (int j = 0; S; ++j) {  // j: ordinal of the run
     int s;
     uint32_t R = pcs_pop_run(c.F, S, s);
     unsigned long long T = ((unsigned long long)(c.U & R)) << 1;
@@ -290,8 +283,9 @@ __global__ void __launch_bounds__(PCS_CCL_THREADS) k_ccl_merge_edges(P prov, int
       int rel = (i - 1) >> 5;
       if (!(top || (rel < 0 && left) || (rel > 0 && right))) continue;  // done inside the tile
       int ja = (i - 1) & 31;
-      int sa = pcs_start_at_or_below(c.Sa[rel + 1], ja);
-      pcs_uf_union(par, base + s, abase + rel * 32 + sa);
+      const uint32_t Sa = c.Sa[rel + 1];
+      int sa = pcs_start_at_or_below(Sa, ja);
+      pcs_uf_union<LSPW>(par, NW, pcs_node<LSPW>(gw, j), pcs_node<LSPW>(gw - WW + rel, pcs_run_ord(Sa, sa)));
     }
   }
 }
@@ -310,10 +304,11 @@ __global__ void __launch_bounds__(PCS_CCL_THREADS)
   if (2 * pair >= nchunks) return;
   const long long b = blockIdx.y;
   P p = prov.slice(b);
-  const int Wp = WW << 5;
-  int* par = parent + b * (long long)H * Wp;
-  uint32_t Sw[2] = {0u, 0u}, roots[2] = {0u, 0u};
-  int base[2] = {0, 0}, kk[2], yy[2];
+  constexpr int LSPW = PcsNodes<P>::LOG_SPW;
+  const int NW = H * WW;
+  int* par = parent + b * ((long long)NW << LSPW);
+  uint32_t roots[2] = {0u, 0u};
+  int gw[2] = {0, 0}, nr[2] = {0, 0}, kk[2], yy[2];
   bool valid[2];
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
@@ -323,40 +318,36 @@ __global__ void __launch_bounds__(PCS_CCL_THREADS)
     yy[u] = g32 / CPR;
     kk[u] = ch * 32 + lane;
     if (valid[u] && kk[u] < WW) {
-      uint32_t F;
-      p.FS(yy[u], kk[u], F, Sw[u]);
-      base[u] = yy[u] * Wp + (kk[u] << 5);
+      uint32_t F, S;
+      p.FS(yy[u], kk[u], F, S);
+      nr[u] = __popc(S);
+      gw[u] = yy[u] * WW + kk[u];
     }
   }
-  while (Sw[0] | Sw[1]) {
+  for (int j = 0; j < nr[0] || j < nr[1]; ++j) {  // j: run ordinal, both words side by side
     int n[2], r[2], q[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      n[u] = -1;
-      if (Sw[u]) {
-        const int s = __ffs(Sw[u]) - 1;
-        Sw[u] &= Sw[u] - 1;
-        n[u] = base[u] + s;
-      }
+      n[u] = j < nr[u] ? pcs_node<LSPW>(gw[u], j) : -1;
       r[u] = n[u];
-      q[u] = n[u] >= 0 ? pcs_ld_cg(par + n[u]) : -1;
+      q[u] = n[u] >= 0 ? pcs_ld_cg(par + j * NW + gw[u]) : -1;
     }
     while (q[0] != r[0] || q[1] != r[1]) {
 #pragma unroll
       for (int u = 0; u < 2; ++u)
         if (q[u] != r[u]) {
           r[u] = q[u];
-          q[u] = pcs_ld_cg(par + r[u]);
+          q[u] = pcs_ld_cg(par + pcs_slot<LSPW>(r[u], NW));
         }
     }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       if (n[u] < 0) continue;
       if (r[u] != n[u])
-        par[n[u]] = r[u];
+        par[j * NW + gw[u]] = r[u];
       else {
-        roots[u] |= 1u << (n[u] - base[u]);
-        if (aux) aux[b * (long long)H * Wp + n[u]] = 0;
+        roots[u] |= 1u << j;
+        if (aux) aux[b * ((long long)NW << LSPW) + j * NW + gw[u]] = 0;
       }
     }
   }
@@ -430,10 +421,11 @@ __global__ void __launch_bounds__(1024) k_ccl_offsets(const int32_t* __restrict_
 
 // warp per chunk: roots get their raster-order rank (stored negated in parent),
 // and the table's first-pixel column if requested
+template <class P>
 __global__ void __launch_bounds__(PCS_CCL_THREADS)
-    k_ccl_rank(int* __restrict__ parent, const uint32_t* __restrict__ rootbits, const int* __restrict__ chunk,
-               const int* __restrict__ offsets, long long* __restrict__ first_out, long long cap, int B, int H, int W,
-               int WW, int CPR) {
+    k_ccl_rank(P prov, int* __restrict__ parent, const uint32_t* __restrict__ rootbits, const int* __restrict__ chunk,
+               const int* __restrict__ offsets, long long* __restrict__ first_out, long long cap, int B, int CPR) {
+  const int H = prov.H, WW = prov.WW, W = prov.W;
   const int g32 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // 32-word chunk of the slice; the slice is blockIdx.y
   int lane = threadIdx.x & 31;
   if (g32 >= H * CPR) return;
@@ -441,31 +433,34 @@ __global__ void __launch_bounds__(PCS_CCL_THREADS)
   const long long g = b * H * CPR + g32;
   const int ch = g32 % CPR, y = g32 / CPR;
   int k = ch * 32 + lane;
-  uint32_t roots = k < WW ? rootbits[(b * H + y) * (long long)WW + k] : 0u;
+  uint32_t roots = k < WW ? rootbits[(b * H + y) * (long long)WW + k] : 0u;  // bit j: run of ordinal j is a root
   const int cbase = chunk[g];  // requested beside the root bits, not after the scan
   int tot;
   int ex = pcs_warp_excl_scan(__popc(roots), lane, &tot);
   if (!roots) return;
   int rank = cbase + ex;
-  const int Wp = WW << 5;
-  int* par = parent + b * (long long)H * Wp;
-  int base = y * Wp + (k << 5);
+  constexpr int LSPW = PcsNodes<P>::LOG_SPW;
+  const int NW = H * WW;
+  int* par = parent + b * ((long long)NW << LSPW);
+  const int gw = y * WW + k;
   long long trow = first_out ? (long long)offsets[b] : 0;
+  uint32_t S = 0;
+  if (first_out) {
+    uint32_t F;
+    prov.slice(b).FS(y, k, F, S);
+  }
   while (roots) {
-    int s = __ffs(roots) - 1;
+    int j = __ffs(roots) - 1;
     roots &= roots - 1;
     ++rank;
-    par[base + s] = -rank;
+    par[j * NW + gw] = -rank;
     if (first_out) {
       long long row = trow + rank - 1;
-      if (row < cap) first_out[row] = (long long)y * W + (k << 5) + s;
+      uint32_t sb = S;  // start bit of the run of ordinal j: drop the j lowest start bits
+      for (int q = 0; q < j; ++q) sb &= sb - 1;
+      if (row < cap) first_out[row] = (long long)y * W + (k << 5) + (__ffs(sb) - 1);
     }
   }
-}
-
-__device__ __forceinline__ int pcs_label_of(const int* par, int node) {
-  int p = par[node];
-  return p < 0 ? -p : -par[p];
 }
 
 // warp per chunk: expand run labels to pixels with coalesced 128-byte stores
@@ -483,19 +478,20 @@ __global__ void __launch_bounds__(PCS_CCL_THREADS)
   int k = ch * 32 + lane;
   uint32_t F = 0, S = 0;
   int one = 0;  // label of the word's only run (words with several runs go through shared memory)
-  const int Wp = WW << 5;
-  const int* par = parent + b * (long long)H * Wp;
+  constexpr int LSPW = PcsNodes<P>::LOG_SPW;
+  const int NW = H * WW;
+  const int* par = parent + b * ((long long)NW << LSPW);
   if (k < WW) {
     P p = prov.slice(b);
     p.FS(y, k, F, S);
-    int base = y * Wp + (k << 5);
+    const int gw = y * WW + k;
     uint32_t rem = S;
     if (rem && !(rem & (rem - 1))) {
-      const int p0 = par[base + __ffs(rem) - 1];
-      one = p0 < 0 ? -p0 : -par[p0];
+      const int p0 = par[gw];  // plane 0: the word's only run
+      one = p0 < 0 ? -p0 : -par[pcs_slot<LSPW>(p0, NW)];
       rem = 0;
     }
-    while (rem) {  // four independent lookups in flight per iteration
+    for (int j = 0; rem; j += 4) {  // four independent lookups in flight per iteration; j: ordinal of the first
       int s0 = __ffs(rem) - 1;
       rem &= rem - 1;
       int s1 = rem ? __ffs(rem) - 1 : -1;
@@ -504,14 +500,14 @@ __global__ void __launch_bounds__(PCS_CCL_THREADS)
       rem &= rem - 1 + (rem == 0);
       int s3 = rem ? __ffs(rem) - 1 : -1;
       rem &= rem - 1 + (rem == 0);
-      int p0 = par[base + s0];
-      int p1 = s1 >= 0 ? par[base + s1] : -1;
-      int p2 = s2 >= 0 ? par[base + s2] : -1;
-      int p3 = s3 >= 0 ? par[base + s3] : -1;
-      int l0 = p0 < 0 ? -p0 : -par[p0];
-      int l1 = p1 < 0 ? -p1 : -par[p1];
-      int l2 = p2 < 0 ? -p2 : -par[p2];
-      int l3 = p3 < 0 ? -p3 : -par[p3];
+      int p0 = par[j * NW + gw];
+      int p1 = s1 >= 0 ? par[(j + 1) * NW + gw] : -1;
+      int p2 = s2 >= 0 ? par[(j + 2) * NW + gw] : -1;
+      int p3 = s3 >= 0 ? par[(j + 3) * NW + gw] : -1;
+      int l0 = p0 < 0 ? -p0 : -par[pcs_slot<LSPW>(p0, NW)];
+      int l1 = p1 < 0 ? -p1 : -par[pcs_slot<LSPW>(p1, NW)];
+      int l2 = p2 < 0 ? -p2 : -par[pcs_slot<LSPW>(p2, NW)];
+      int l3 = p3 < 0 ? -p3 : -par[pcs_slot<LSPW>(p3, NW)];
       lab[wl][lane][s0] = l0;
       if (s1 >= 0) lab[wl][lane][s1] = l1;
       if (s2 >= 0) lab[wl][lane][s2] = l2;
@@ -589,8 +585,9 @@ __global__ void __launch_bounds__(PCS_CCL_THREADS)
     if (k0 + i < WW) p.FS(y, k0 + i, F4[i], S4[i]);
   }
   if (!(S4[0] | S4[1] | S4[2] | S4[3])) return;
-  const int Wp = WW << 5;
-  int* par = parent + b * (long long)H * Wp;
+  constexpr int LSPW = PcsNodes<P>::LOG_SPW;
+  const int NW = H * WW;
+  int* par = parent + b * ((long long)NW << LSPW);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     uint32_t F = F4[i], S = S4[i];
@@ -606,15 +603,14 @@ __global__ void __launch_bounds__(PCS_CCL_THREADS)
     }
     M &= F;
     if (!M) continue;
-    const int base = y * Wp + (k << 5);
-    while (S) {
+    const int gw = y * WW + k;
+    for (int j = 0; S; ++j) {  // j: ordinal of the run
       int s;
       uint32_t R = pcs_pop_run(F, S, s);
       if (!(R & M)) continue;
-      int n = base + s;
-      int q = par[n];
-      if (q < 0) continue;  // already a marked root
-      par[q] = PCS_MARK;     // q is the root (q == n for a root)
+      int q = par[j * NW + gw];
+      if (q < 0) continue;                      // already a marked root
+      par[pcs_slot<LSPW>(q, NW)] = PCS_MARK;    // q is the root (its own id for a root)
     }
   }
 }
@@ -632,35 +628,34 @@ __global__ void __launch_bounds__(PCS_CCL_THREADS) k_ccl_area(P prov, const int*
   uint32_t F, S;
   p.FS(y, k, F, S);
   if (!S) return;
-  const int Wp = WW << 5;
-  const int* par = parent + b * (long long)H * Wp;
-  int* ax = aux + b * (long long)H * Wp;
-  int base = y * Wp + (k << 5);
-  while (S) {
+  constexpr int LSPW = PcsNodes<P>::LOG_SPW;
+  const int NW = H * WW;
+  const int* par = parent + b * ((long long)NW << LSPW);
+  int* ax = aux + b * ((long long)NW << LSPW);
+  const int gw = y * WW + k;
+  for (int j = 0; S; ++j) {
     int s;
     uint32_t R = pcs_pop_run(F, S, s);
-    atomicAdd(ax + par[base + s], __popc(R));
+    atomicAdd(ax + pcs_slot<LSPW>(par[j * NW + gw], NW), __popc(R));  // after the flatten every node holds its root's id
   }
 }
 
 // thread per word: mark roots whose accumulated area is below min_size
+template <int LSPW>
 __global__ void __launch_bounds__(PCS_CCL_THREADS)
     k_ccl_mark_small(int* __restrict__ parent, const uint32_t* __restrict__ rootbits, const int* __restrict__ aux,
                      int min_size, int B, int H, int WW) {
-  const int t32 = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t32 >= H * WW) return;
+  const int t32 = blockIdx.x * blockDim.x + threadIdx.x;  // word of the slice
+  const int NW = H * WW;
+  if (t32 >= NW) return;
   const long long b = blockIdx.y;
-  const long long t = b * H * WW + t32;
-  uint32_t roots = rootbits[t];
+  uint32_t roots = rootbits[b * NW + t32];  // bit j: run of ordinal j is a root
   if (!roots) return;
-  const int k = t32 % WW, y = t32 / WW;
-  const int Wp = WW << 5;
-  long long sb = b * (long long)H * Wp;
-  int base = y * Wp + (k << 5);
+  const long long sb = b * ((long long)NW << LSPW);
   while (roots) {
-    int s = __ffs(roots) - 1;
+    int j = __ffs(roots) - 1;
     roots &= roots - 1;
-    if (aux[sb + base + s] < min_size) parent[sb + base + s] = PCS_MARK;
+    if (aux[sb + j * NW + t32] < min_size) parent[sb + j * NW + t32] = PCS_MARK;
   }
 }
 
@@ -682,15 +677,15 @@ __global__ void __launch_bounds__(PCS_CCL_THREADS)
   p.FS(y, k, F, S);
   uint32_t o = 0;
   if (S && !(veto_counts && veto_counts[b] == 1)) {
-    const int Wp = WW << 5;
-    const int* par = parent + b * (long long)H * Wp;
-    int base = y * Wp + (k << 5);
-    while (S) {
+    constexpr int LSPW = PcsNodes<P>::LOG_SPW;
+    const int NW = H * WW;
+    const int* par = parent + b * ((long long)NW << LSPW);
+    const int gw = y * WW + k;
+    for (int j = 0; S; ++j) {
       int s;
       uint32_t R = pcs_pop_run(F, S, s);
-      int n = base + s;
-      int q = par[n];
-      int marked = q < 0 ? 1 : (q == n ? 0 : (par[q] < 0));
+      int q = par[j * NW + gw];
+      int marked = q < 0 ? 1 : (q == pcs_node<LSPW>(gw, j) ? 0 : (par[pcs_slot<LSPW>(q, NW)] < 0));
       if (marked == want_marked) o |= R;
     }
   }
@@ -971,7 +966,7 @@ static int ccl_label(const P& prov, int B, int conn, void* labels, int label_byt
   if (rc) return rc;
   const int H = prov.H, WW = prov.WW, CPR = (WW + 31) / 32;
   dim3 gc(pcs_blocks((long long)H * CPR * 32, PCS_CCL_THREADS), B);
-  PCS_LAUNCH("k_ccl_rank", st, k_ccl_rank<<<gc, PCS_CCL_THREADS, 0, st>>>(ws.parent, ws.rootbits, ws.chunk, ws.offsets, first_out, cap, B, H, prov.W, WW, CPR));
+  PCS_LAUNCH("k_ccl_rank", st, k_ccl_rank<P><<<gc, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, ws.rootbits, ws.chunk, ws.offsets, first_out, cap, B, CPR));
   if (label_bytes == 4)
     PCS_LAUNCH("k_ccl_relabel", st, k_ccl_relabel<P, int32_t><<<gc, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, (int32_t*)labels, B, CPR));
   else
@@ -1121,7 +1116,7 @@ int pcs_remove_small_bits(const uint32_t* bits, uint32_t* out, int B, int H, int
   dim3 gw(pcs_blocks((long long)H * prov.WW, PCS_CCL_THREADS), B);
   dim3 gq(pcs_blocks((long long)H * ((prov.WW + 3) / 4), PCS_CCL_THREADS), B);  // groups of 4 words
   PCS_LAUNCH("k_ccl_area", st, k_ccl_area<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, ws.aux, B));
-  PCS_LAUNCH("k_ccl_mark_small", st, k_ccl_mark_small<<<gw, PCS_CCL_THREADS, 0, st>>>(ws.parent, ws.rootbits, ws.aux, min_size, B, H, prov.WW));
+  PCS_LAUNCH("k_ccl_mark_small", st, k_ccl_mark_small<PcsNodes<PcsBinProv>::LOG_SPW><<<gw, PCS_CCL_THREADS, 0, st>>>(ws.parent, ws.rootbits, ws.aux, min_size, B, H, prov.WW));
   PCS_LAUNCH("k_ccl_select", st, k_ccl_select<PcsBinProv><<<gw, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, 0, nullptr, nullptr, out, nullptr, B));
   return pcs_check_launch("remove small objects");
 }

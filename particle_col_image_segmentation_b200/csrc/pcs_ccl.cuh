@@ -10,11 +10,22 @@
 // word with bit masks -- F (foreground), S (starts of within-word runs of equal
 // value), U / UL / UR (pixel equals its upper / upper-left / upper-right
 // neighbour) and J (pixel 0 continues the run of the previous word).  Nodes of
-// the union-find forest are the run starts only, so parent traffic is sparse
-// and lives in L2.  Union keeps the smaller raster index as root (atomicMin),
-// which makes every root the first raster pixel of its component: numbering
-// roots in raster order (a two-level scan over 32-word chunks) reproduces
-// scipy / scikit-image label order bit-exactly.
+// the union-find forest are the within-word runs only.
+//
+// Node ids and storage.  id = word * SPW + ordinal, where word = y * WW + k is the
+// slice-local word index and ordinal counts the runs of that word that start below
+// it (SPW = 16 for binary masks -- a 32-bit word holds at most 16 runs -- and 32 for
+// multi-valued images).  Ids ascend in raster order of the runs' first pixels, so
+// a union that keeps the smaller id as root (atomicMin) makes every root the first
+// raster pixel of its component: numbering roots in id order (a two-level scan over
+// 32-word chunks) reproduces scipy / scikit-image label order bit-exactly.
+// Parents are stored PLANE-MAJOR: slot(id) = ordinal * NW + word (NW = H * WW).
+// Plane 0 -- the first run of every word, 96 % of all runs on blob-like masks -- is a
+// dense int32 image of 4 B per word (0.125 B / pixel) that stays in L2 and shares
+// sectors between neighbouring words; the other planes are touched only where a
+// word really has several runs.  (Round 1 addressed a node by the pixel position of
+// its run start, one int per PIXEL: every parent access was its own 64-byte DRAM
+// transaction, and the pointer-chasing kernels were bound by exactly that.)
 #pragma once
 #include "pcs_common.cuh"
 
@@ -113,29 +124,37 @@ __device__ __forceinline__ uint32_t pcs_pop_run(uint32_t F, uint32_t& S, int& s)
   return m << s;
 }
 
+// -------------------------------------------------------------- node ids
+template <class P> struct PcsNodes { static constexpr int LOG_SPW = 4; };            // binary masks: <= 16 runs per word
+template <> struct PcsNodes<PcsGenProv> { static constexpr int LOG_SPW = 5; };       // multi-valued: <= 32
+template <int LSPW> __device__ __forceinline__ int pcs_node(int word, int ord) { return (word << LSPW) | ord; }
+template <int LSPW> __device__ __forceinline__ int pcs_slot(int id, int NW) { return (id & ((1 << LSPW) - 1)) * NW + (id >> LSPW); }
+// ordinal of the run of S (run-start word) that starts at bit s
+__device__ __forceinline__ int pcs_run_ord(uint32_t S, int s) { return __popc(S & ((1u << s) - 1u)); }
+
 // -------------------------------------------------------------- union-find
-__device__ __forceinline__ int pcs_uf_find(int* par, int n) {
-  int r = n, p = pcs_ld_cg(par + r);
+template <int LSPW> __device__ __forceinline__ int pcs_uf_find(int* par, int NW, int n) {
+  int r = n, p = pcs_ld_cg(par + pcs_slot<LSPW>(r, NW));
   int first = p;
   while (p != r) {
     r = p;
-    p = pcs_ld_cg(par + r);
+    p = pcs_ld_cg(par + pcs_slot<LSPW>(r, NW));
   }
-  if (first != r) atomicMin(par + n, r);  // one-step compression (monotone, race-safe)
+  if (first != r) atomicMin(par + pcs_slot<LSPW>(n, NW), r);  // one-step compression (monotone, race-safe)
   return r;
 }
 
-__device__ __forceinline__ void pcs_uf_union(int* par, int a, int b) {
+template <int LSPW> __device__ __forceinline__ void pcs_uf_union(int* par, int NW, int a, int b) {
   while (true) {
-    a = pcs_uf_find(par, a);
-    b = pcs_uf_find(par, b);
+    a = pcs_uf_find<LSPW>(par, NW, a);
+    b = pcs_uf_find<LSPW>(par, NW, b);
     if (a == b) return;
     if (a < b) {
       int t = a;
       a = b;
       b = t;
     }
-    int old = atomicMin(par + a, b);  // link the larger root under the smaller
+    int old = atomicMin(par + pcs_slot<LSPW>(a, NW), b);  // link the larger root under the smaller
     if (old == a) return;
     a = old;  // a had been linked meanwhile: keep uniting its (old) parent with b
   }
@@ -143,11 +162,11 @@ __device__ __forceinline__ void pcs_uf_union(int* par, int a, int b) {
 
 // Workspace layout of one connected-component job.
 struct PcsCclWs {
-  int* parent;         // B * H * Wp
-  uint32_t* rootbits;  // B * H * WW
+  int* parent;         // B * SPW * NW ints in use (B * H * Wp allocated: enough for SPW = 32)
+  uint32_t* rootbits;  // B * H * WW  (bit j: the word's run of ordinal j is a root)
   int* chunk;          // B * H * CPR  (roots per 32-word chunk, then exclusive base)
   int* offsets;        // B + 1        (exclusive scan of per-slice counts)
-  int* aux;            // B * H * Wp   (optional: per-root accumulators, e.g. area)
+  int* aux;            // like parent   (optional: per-root accumulators, e.g. area)
 };
 
 size_t pcs_ccl_ws_bytes(int B, int H, int W, int with_aux);

@@ -98,6 +98,11 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MINBLOCKS)
         if (have_next) cur[v] = __ldg(n4 + v * HIST_THREADS);
       }
     } else {  // ragged tail or unaligned slice
+      if (have_next) {  // the next tile (first of the next slice) still wants its vectors in flight
+        const uint4* n4 = reinterpret_cast<const uint4*>(nsrc + nstart) + tid;
+#pragma unroll
+        for (int v = 0; v < HIST_VEC_PER_THREAD; ++v) cur[v] = __ldg(n4 + v * HIST_THREADS);
+      }
       const long long end = min(npix, start + HIST_PIX_PER_BLOCK);
       for (long long i = start + tid; i < end; i += HIST_THREADS) {
         const uint32_t a = src[i];
