@@ -126,3 +126,58 @@ __device__ __forceinline__ void pcs_store_mask_bytes(uint8_t* __restrict__ row, 
   }
 }
 
+// ---------------------------------------------------------------- binary 5x5 median helpers (scipy 'reflect' borders)
+__device__ __forceinline__ int pcs_reflect(int i, int n) {
+  // scipy.ndimage mode='reflect': (d c b a | a b c d | d c b a)
+  if (i < 0) i = -i - 1;
+  if (i >= n) i = 2 * n - i - 1;
+  return i;
+}
+
+__device__ __forceinline__ uint32_t pcs_getbit(const uint32_t* row, int x) { return (row[x >> 5] >> (x & 31)) & 1u; }
+
+// 64-bit window of a bit row: window bit i <-> x = 32k - 16 + i, reflected at the row ends
+__device__ __forceinline__ unsigned long long pcs_window_reflect(const uint32_t* row, int k, int W, int WW, int r) {
+  unsigned long long win = (unsigned long long)row[k] << 16;
+  if (k > 0) win |= row[k - 1] >> 16;
+  if (k + 1 < WW) win |= (unsigned long long)(row[k + 1] & 0xffffu) << 48;
+  if (k == 0)
+    for (int q = 1; q <= r; ++q) win |= (unsigned long long)pcs_getbit(row, q - 1) << (16 - q);
+  const int xhi = (k << 5) + 47;
+  if (xhi >= W)
+    for (int q = 1; q <= r; ++q) {
+      int x = W - 1 + q;
+      int i = x - (k << 5) + 16;
+      if (i >= 0 && i < 64) win |= (unsigned long long)pcs_getbit(row, W - q) << i;
+    }
+  return win;
+}
+
+// 5x5 binary median, bit-sliced: the 25 neighbours of 32 pixels are counted with carry-save
+// adders on whole words (about 8 instructions per pixel instead of one popc per pixel and row).
+__device__ __forceinline__ void pcs_add5(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t& s0, uint32_t& s1,
+                                         uint32_t& s2) {
+  const uint32_t t = a ^ b ^ c, m1 = (a & b) | (c & (a ^ b));
+  s0 = t ^ d ^ e;
+  const uint32_t m2 = (t & d) | (e & (t ^ d));
+  s1 = m1 ^ m2;
+  s2 = m1 & m2;
+}
+
+// the five rows' bit-sliced horizontal counts (r0 = ones, r1 = twos, r2 = fours) -> bits where at least 13 of the
+// 25 neighbours are set (the median of a 5x5 binary window)
+__device__ __forceinline__ uint32_t pcs_majority5_word(const uint32_t (&r0)[5], const uint32_t (&r1)[5], const uint32_t (&r2)[5]) {
+  uint32_t a0, a1, a2, b1, b2, b3, c2, c3, c4;
+  pcs_add5(r0[0], r0[1], r0[2], r0[3], r0[4], a0, a1, a2);  // ones   (weight 1)
+  pcs_add5(r1[0], r1[1], r1[2], r1[3], r1[4], b1, b2, b3);  // twos   (weight 2)
+  pcs_add5(r2[0], r2[1], r2[2], r2[3], r2[4], c2, c3, c4);  // fours  (weight 4)
+  // total = A + 2B + 4C, bit by bit
+  const uint32_t s0 = a0;
+  const uint32_t s1 = a1 ^ b1, k2 = a1 & b1;
+  const uint32_t t2 = a2 ^ b2 ^ c2, m2 = (a2 & b2) | (c2 & (a2 ^ b2));
+  const uint32_t s2 = t2 ^ k2, n2 = t2 & k2;
+  const uint32_t t3 = b3 ^ c3 ^ m2, m3 = (b3 & c3) | (m2 & (b3 ^ c3));
+  const uint32_t s3 = t3 ^ n2, n3 = t3 & n2;
+  const uint32_t s4 = c4 ^ m3 ^ n3;
+  return s4 | (s3 & s2 & (s1 | s0));  // total >= 13
+}

@@ -71,32 +71,7 @@ __global__ void __launch_bounds__(MORPH_THREADS)
 }
 
 // ---------------------------------------------------------------- median
-__device__ __forceinline__ int pcs_reflect(int i, int n) {
-  // scipy.ndimage mode='reflect': (d c b a | a b c d | d c b a)
-  if (i < 0) i = -i - 1;
-  if (i >= n) i = 2 * n - i - 1;
-  return i;
-}
-
-__device__ __forceinline__ uint32_t pcs_getbit(const uint32_t* row, int x) { return (row[x >> 5] >> (x & 31)) & 1u; }
-
-// 64-bit window of a bit row: window bit i <-> x = 32k - 16 + i, reflected at the row ends
-__device__ __forceinline__ unsigned long long pcs_window_reflect(const uint32_t* row, int k, int W, int WW, int r) {
-  unsigned long long win = (unsigned long long)row[k] << 16;
-  if (k > 0) win |= row[k - 1] >> 16;
-  if (k + 1 < WW) win |= (unsigned long long)(row[k + 1] & 0xffffu) << 48;
-  if (k == 0)
-    for (int q = 1; q <= r; ++q) win |= (unsigned long long)pcs_getbit(row, q - 1) << (16 - q);
-  const int xhi = (k << 5) + 47;
-  if (xhi >= W)
-    for (int q = 1; q <= r; ++q) {
-      int x = W - 1 + q;
-      int i = x - (k << 5) + 16;
-      if (i >= 0 && i < 64) win |= (unsigned long long)pcs_getbit(row, W - q) << i;
-    }
-  return win;
-}
-
+// (pcs_reflect / pcs_window_reflect / pcs_add5 / pcs_majority5_word live in pcs_common.cuh: the fused pipeline kernel uses them too)
 // binary median (majority) of a size x size window, mode reflect; thread per word
 template <int size>
 __global__ void __launch_bounds__(MORPH_THREADS)
@@ -124,17 +99,6 @@ __global__ void __launch_bounds__(MORPH_THREADS)
   out[t] = o & pcs_valid_mask(k, W);
 }
 
-// 5x5 binary median, bit-sliced: the 25 neighbours of 32 pixels are counted with carry-save
-// adders on whole words (about 8 instructions per pixel instead of one popc per pixel and row).
-__device__ __forceinline__ void pcs_add5(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t& s0, uint32_t& s1,
-                                         uint32_t& s2) {
-  const uint32_t t = a ^ b ^ c, m1 = (a & b) | (c & (a ^ b));
-  s0 = t ^ d ^ e;
-  const uint32_t m2 = (t & d) | (e & (t ^ d));
-  s1 = m1 ^ m2;
-  s2 = m1 & m2;
-}
-
 #define MAJ_ROWS 8  // output rows per thread: each input row's horizontal sums are computed once and reused 5 times
 __global__ void __launch_bounds__(MORPH_THREADS)
     k_majority5_bits(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint8_t* __restrict__ mask, int B, int H, int W,
@@ -160,20 +124,7 @@ __global__ void __launch_bounds__(MORPH_THREADS)
     if (i >= 4) {
       const int y = y0 + i - 4;  // output row whose 5 input rows are now in the window
       if (y < H) {
-        uint32_t a0, a1, a2, b1, b2, b3, c2, c3, c4;
-        pcs_add5(r0[0], r0[1], r0[2], r0[3], r0[4], a0, a1, a2);  // ones   (weight 1)
-        pcs_add5(r1[0], r1[1], r1[2], r1[3], r1[4], b1, b2, b3);  // twos   (weight 2)
-        pcs_add5(r2[0], r2[1], r2[2], r2[3], r2[4], c2, c3, c4);  // fours  (weight 4)
-        // total = A + 2B + 4C, bit by bit
-        const uint32_t s0 = a0;
-        const uint32_t s1 = a1 ^ b1, k2 = a1 & b1;
-        const uint32_t t2 = a2 ^ b2 ^ c2, m2 = (a2 & b2) | (c2 & (a2 ^ b2));
-        const uint32_t s2 = t2 ^ k2, n2 = t2 & k2;
-        const uint32_t t3 = b3 ^ c3 ^ m2, m3 = (b3 & c3) | (m2 & (b3 ^ c3));
-        const uint32_t s3 = t3 ^ n2, n3 = t3 & n2;
-        const uint32_t s4 = c4 ^ m3 ^ n3;
-        // median is 1 when at least 13 of the 25 are set: total >= 13
-        const uint32_t ge13 = (s4 | (s3 & s2 & (s1 | s0))) & vm;
+        const uint32_t ge13 = pcs_majority5_word(r0, r1, r2) & vm;
         out[(b * H + y) * (long long)WW + k] = ge13;
         if (mask) pcs_store_mask_bytes(mask + (b * H + y) * (long long)W, k, W, ge13);  // fused uint8 output
       }

@@ -4,7 +4,7 @@
 // (oracle/pipeline.py states the same composition on the CPU; each stage cites the
 // reference line it stands in for in its own file).  Issuing all ~30 launches from C keeps
 // the stream saturated: no interpreter or allocator work sits between two kernels.
-#include "pcs_common.cuh"
+#include "pcs_ccl.cuh"
 
 #include "pcs.h"
 
@@ -16,6 +16,7 @@ struct SegWs {
   size_t ccl_bytes;
   void* edt;
   size_t edt_bytes;
+  int* rsum;  // per-run intensity sums, laid out like the labeller's parent planes
 };
 
 size_t seg_carve(void* ws, int B, int H, int W, SegWs* out) {
@@ -37,6 +38,7 @@ size_t seg_carve(void* ws, int B, int H, int W, SegWs* out) {
   w.ccl = take(w.ccl_bytes);
   w.edt_bytes = pcs_edt_workspace_bytes(B, H, W);
   w.edt = take(w.edt_bytes);
+  w.rsum = (int*)take((size_t)B * H * pcs_words(W) * 16 * 4);
   if (out) *out = w;
   return n;
 }
@@ -63,16 +65,30 @@ int pcs_segment_chunk(const uint16_t* img, int B, int H, int W, int denoise_size
   STEP(pcs_histogram_u16(img, w.hist, B, H, W, stream));
   STEP(pcs_otsu_u16(w.hist, thr, nullptr, B, (int64_t)H * W, stream));
   const uint32_t* bits = w.raw;
-  STEP(pcs_compare_u16(img, 0, thr, 0, w.raw, nullptr, B, H, W, stream));
-  if (denoise_size > 1) {
-    STEP(pcs_majority_bits_mask(w.raw, w.bits, mask, denoise_size, B, H, W, stream));  // bits + uint8 mask in one pass
+  // fused path (default parameters, images at least as large as the median window): the image is read once more,
+  // by the kernel that thresholds, denoises, writes the mask and runs the labeller's tile pass
+  const bool fused = (denoise_size == 5 || denoise_size <= 1) && H >= 5 && W >= 5 && H <= 16384 && W <= 16384 && B <= 65535;
+  if (fused) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PcsCclWs cw;
+    STEP(pcs_ccl_ws_carve(w.ccl, w.ccl_bytes, B, H, W, 0, &cw));
     bits = w.bits;
+    STEP(pcs_seg_threshold_tile(img, thr, denoise_size == 5, w.bits, mask, cw.parent, w.rsum, B, H, W, st));
+    STEP(pcs_ccl_bin_forest_from_tiles(w.bits, B, H, W, cw, counts, st));
+    STEP(pcs_seg_rank_relabel_table(w.bits, cw, w.rsum, table, cap, labels, B, H, W, st));
+    cudaMemcpyAsync(offsets, cw.offsets, (size_t)(B + 1) * 4, cudaMemcpyDeviceToDevice, st);
   } else {
-    STEP(pcs_unpack_bits(bits, mask, B, H, W, stream));
+    STEP(pcs_compare_u16(img, 0, thr, 0, w.raw, nullptr, B, H, W, stream));
+    if (denoise_size > 1) {
+      STEP(pcs_majority_bits_mask(w.raw, w.bits, mask, denoise_size, B, H, W, stream));  // bits + uint8 mask in one pass
+      bits = w.bits;
+    } else {
+      STEP(pcs_unpack_bits(bits, mask, B, H, W, stream));
+    }
+    STEP(pcs_label_bits(bits, B, H, W, 8, 0, labels, 4, counts, offsets, nullptr, 0, w.ccl, w.ccl_bytes, stream));
+    STEP(pcs_table_init_rows(table, cap, offsets, B, stream));
+    STEP(pcs_region_table(labels, 4, img, 1, bits, nullptr, offsets, table, cap, B, H, W, stream));
   }
-  STEP(pcs_label_bits(bits, B, H, W, 8, 0, labels, 4, counts, offsets, nullptr, 0, w.ccl, w.ccl_bytes, stream));
-  STEP(pcs_table_init_rows(table, cap, offsets, B, stream));
-  STEP(pcs_region_table(labels, 4, img, 1, bits, nullptr, offsets, table, cap, B, H, W, stream));
   if (ftable) STEP(pcs_table_finalize(table, cap, offsets, B, W, (double)z0, ftable, stream));
   // small objects out and holes filled in one call: areas come from the table just built, and only
   // row gaps between two runs of one label can hold hole pixels

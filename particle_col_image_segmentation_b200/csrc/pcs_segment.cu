@@ -1,0 +1,522 @@
+// Fused kernels of the z-stack segment pipeline (pcs_segment_chunk).  Each one merges stages that the
+// drop-in primitives run as separate passes, so that a pixel, a mask word or a run label crosses HBM once:
+//
+//   k_seg_threshold_tile   image > Otsu threshold -> 5x5 binary median -> uint8 mask + bit rows
+//                          -> tile-local union-find of the runs (the first pass of the labeller)
+//                          -> per-run intensity sums.  The uint16 image is read here for the last time.
+//                          (ilastik's role + scipy.ndimage.median_filter, tiff_analysis.py:122, :643;
+//                           skimage.measure.label pass 1, tiff_analysis.py:743)
+//   k_seg_rank_init        roots get their raster-order label; the root's table row is initialised with the
+//                          fields a root knows by itself (first pixel, top row)
+//   k_seg_relabel_table    run labels -> int32 label image (16-byte coalesced stores) and, from the same
+//                          registers, the per-label reductions (regionprops area / centroid sums / bbox /
+//                          integrated intensity, tiff_analysis.py:746-773); the label of every run is left in
+//                          the parent plane for the refine stage
+//
+// Round 1 ran k_compare, k_majority5_bits, k_ccl_tile, k_table_init, k_ccl_rank, k_ccl_relabel and
+// k_region_table_bits for this: the image was read three times, the label image written and re-read.
+#include "pcs_ccl.cuh"
+
+#include "pcs.h"
+
+#define SEG_TR 32  // tile rows   } the labeller's tile (pcs_ccl.cu: PcsTile<PcsBinProv>)
+#define SEG_TW 8   // tile words  }
+#define SEG_THREADS 128
+#define SEG_LSPW 4
+#define SEG_SPW 16
+#define SEG_RR (SEG_TR + 4)  // staged rows: two halo rows above and below
+#define SEG_RW (SEG_TW + 2)  // staged words per row: one halo word left and right (only two bits of each are used)
+
+#define T_AREA 0
+#define T_SUMY 1
+#define T_SUMX 2
+#define T_MINY 3
+#define T_MINX 4
+#define T_MAXY 5
+#define T_MAXX 6
+#define T_FIRST 7
+#define T_SUMI 8
+#define T_OVERLAP 9
+
+__device__ __forceinline__ int seg_lfind(volatile int* sp, int n) {
+  int r = n, p = sp[r];
+  const int first = p;
+  while (p != r) {
+    r = p;
+    p = sp[r];
+  }
+  if (first != r) atomicMin((int*)sp + n, r);
+  return r;
+}
+
+__device__ __forceinline__ void seg_lunion(int* sp, int a, int b) {
+  while (true) {
+    a = seg_lfind(sp, a);
+    b = seg_lfind(sp, b);
+    if (a == b) return;
+    if (a < b) {
+      int t = a;
+      a = b;
+      b = t;
+    }
+    int old = atomicMin(sp + a, b);
+    if (old == a) return;
+    a = old;
+  }
+}
+
+// 8 pixels of a uint4 against the threshold -> 8 bits
+__device__ __forceinline__ uint32_t seg_cmp8(const uint4& q, uint32_t t) {
+  uint32_t m = 0;
+  m |= (uint32_t)((q.x & 0xffffu) > t) << 0;
+  m |= (uint32_t)((q.x >> 16) > t) << 1;
+  m |= (uint32_t)((q.y & 0xffffu) > t) << 2;
+  m |= (uint32_t)((q.y >> 16) > t) << 3;
+  m |= (uint32_t)((q.z & 0xffffu) > t) << 4;
+  m |= (uint32_t)((q.z >> 16) > t) << 5;
+  m |= (uint32_t)((q.w & 0xffffu) > t) << 6;
+  m |= (uint32_t)((q.w >> 16) > t) << 7;
+  return m;
+}
+
+// CTA = one labelling tile (32 rows x 256 pixels) of one slice.
+//  1. stage: rows y0-2 .. y0+33, each as one fully coalesced 512-byte warp load (all of a thread's loads are
+//     issued before the first compare), compared against the slice's threshold and packed to bit rows in shared
+//     memory; the two halo pixels left and right of the tile come from 4-byte loads;
+//  2. median: bit-sliced carry-save count of the 25 neighbours (scipy 'reflect' at the image border), thread =
+//     (word column, pair of rows); the final word goes to the bit plane, the uint8 mask and shared memory;
+//  3. label pass 1 on the words in shared memory: slots per run, unions inside the tile with shared atomics,
+//     every run leaves with the id of its tile-local root (same result as k_ccl_tile<PcsBinProv, 8>);
+//  4. per-run sums of the pixel values (the pixels come back from L1/L2: this CTA has just read them).
+// The memory-bound stage of one CTA overlaps the latency-bound union-find of its neighbours on the SM.
+template <bool MEDIAN>
+__global__ void __launch_bounds__(SEG_THREADS)
+    k_seg_threshold_tile(const uint16_t* __restrict__ img, const int32_t* __restrict__ thr, uint32_t* __restrict__ bits,
+                         uint8_t* __restrict__ mask, int* __restrict__ parent, int* __restrict__ rsum, int H, int W, int WW) {
+  constexpr int NWORDS = SEG_TR * SEG_TW;
+  __shared__ uint32_t raw[SEG_RR][SEG_RW];
+  __shared__ int sp[NWORDS * SEG_SPW];
+  __shared__ uint32_t fsm[NWORDS], ssm[NWORDS];
+  __shared__ unsigned short items[NWORDS];
+  __shared__ int nitems;
+  const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
+  const int k0 = blockIdx.x * SEG_TW, y0 = blockIdx.y * SEG_TR, x0 = k0 << 5;
+  const long long b = blockIdx.z;
+  const uint16_t* src = img + b * (long long)H * W;
+  const uint32_t t = (uint32_t)max(thr[b], 0);  // a negative threshold cannot occur (Otsu of uint16 data)
+  if (tid == 0) nitems = 0;
+  const int halo = MEDIAN ? 2 : 0;
+  // ---------------- 1. stage the raw threshold bits
+  const bool fast = x0 + 32 * SEG_TW <= W && (W & 7) == 0 && ((((uintptr_t)src) & 15) == 0);
+  if (fast) {
+    constexpr int RPW = SEG_RR / 4;  // rows per warp
+    uint4 q[RPW];
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+      const int r = wq + 4 * i, yi = y0 - 2 + r;
+      q[i] = make_uint4(0, 0, 0, 0);
+      if (r >= 2 - halo && r < SEG_TR + 2 + halo && yi >= 0 && yi < H) q[i] = __ldg(reinterpret_cast<const uint4*>(src + (long long)yi * W + x0) + lane);
+    }
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+      const int r = wq + 4 * i;
+      uint32_t v = seg_cmp8(q[i], t) << (8 * (lane & 3));  // lanes 4w .. 4w+3 hold the four bytes of word w
+      v |= __shfl_xor_sync(0xffffffffu, v, 1);
+      v |= __shfl_xor_sync(0xffffffffu, v, 2);
+      if ((lane & 3) == 0) raw[r][1 + (lane >> 2)] = v;
+    }
+  } else {
+    for (int i = tid; i < SEG_RR * SEG_TW; i += SEG_THREADS) {
+      const int r = i / SEG_TW, c = i % SEG_TW, yi = y0 - 2 + r, k = k0 + c;
+      uint32_t v = 0;
+      if (r >= 2 - halo && r < SEG_TR + 2 + halo && yi >= 0 && yi < H && k < WW) {
+        const uint16_t* row = src + (long long)yi * W;
+        const int n = min(32, W - (k << 5));
+        for (int e = 0; e < n; ++e) v |= (uint32_t)(row[(k << 5) + e] > t) << e;
+      }
+      raw[r][1 + c] = v;
+    }
+  }
+  if (MEDIAN && tid < 2 * SEG_RR) {  // halo pixels: x0-2, x0-1 (bits 30, 31 of word k0-1) and x0+256, x0+257 (bits 0, 1 of word k0+8)
+    const int r = tid >> 1, side = tid & 1, yi = y0 - 2 + r;
+    uint32_t v = 0;
+    if (yi >= 0 && yi < H) {
+      const uint16_t* row = src + (long long)yi * W;
+      if (side == 0) {
+        if (x0 >= 2) v = ((uint32_t)(row[x0 - 2] > t) << 30) | ((uint32_t)(row[x0 - 1] > t) << 31);
+      } else {
+        const int xr = x0 + 32 * SEG_TW;
+        if (xr < W) v |= (uint32_t)(row[xr] > t);
+        if (xr + 1 < W) v |= (uint32_t)(row[xr + 1] > t) << 1;
+      }
+    }
+    raw[r][side ? SEG_RW - 1 : 0] = v;
+  }
+  __syncthreads();
+  // ---------------- 2. median + outputs; thread = (word column c, rows 2 * strip and 2 * strip + 1 of the tile)
+  const int c = tid & (SEG_TW - 1), strip = tid >> 3;
+  const int k = k0 + c;
+  uint32_t fin[2] = {0u, 0u};
+  if (k < WW) {
+    const uint32_t vm = pcs_valid_mask(k, W);
+    if (MEDIAN) {
+      uint32_t r0[6], r1[6], r2[6];  // bit-sliced horizontal counts of the six input rows
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const int yi = y0 + 2 * strip - 2 + i;  // input row
+        r0[i] = r1[i] = r2[i] = 0u;
+        if (yi - 2 < H) {  // still needed by an output row of the image
+          const int ry = pcs_reflect(yi, H);
+          const uint32_t* rowp = &raw[ry - (y0 - 2)][1] - k0;  // rowp[k'] = word k' of that row
+          const unsigned long long win = pcs_window_reflect(rowp, k, W, WW, 2);
+          pcs_add5((uint32_t)(win >> 14), (uint32_t)(win >> 15), (uint32_t)(win >> 16), (uint32_t)(win >> 17), (uint32_t)(win >> 18), r0[i],
+                   r1[i], r2[i]);
+        }
+      }
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        const uint32_t a0[5] = {r0[o], r0[o + 1], r0[o + 2], r0[o + 3], r0[o + 4]};
+        const uint32_t a1[5] = {r1[o], r1[o + 1], r1[o + 2], r1[o + 3], r1[o + 4]};
+        const uint32_t a2[5] = {r2[o], r2[o + 1], r2[o + 2], r2[o + 3], r2[o + 4]};
+        if (y0 + 2 * strip + o < H) fin[o] = pcs_majority5_word(a0, a1, a2) & vm;
+      }
+    } else {
+#pragma unroll
+      for (int o = 0; o < 2; ++o)
+        if (y0 + 2 * strip + o < H) fin[o] = raw[2 + 2 * strip + o][1 + c] & vm;
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < 2; ++o) {
+    const int wr = 2 * strip + o, w = wr * SEG_TW + c, y = y0 + wr;
+    const uint32_t F = fin[o];
+    uint32_t S = F & ~(F << 1);
+    fsm[w] = F;
+    ssm[w] = S;
+    if (k < WW && y < H) {
+      bits[(b * H + y) * (long long)WW + k] = F;
+      pcs_store_mask_bytes(mask + (b * H + y) * (long long)W, k, W, F);
+    }
+    const int sbase = w << SEG_LSPW;
+    for (int j = 0; S; ++j) {
+      S &= S - 1;
+      sp[sbase + j] = sbase + j;
+    }
+    // list the non-empty words: one shared atomic per warp
+    const unsigned has = __ballot_sync(0xffffffffu, F != 0u);
+    if (has) {
+      const int leader = __ffs(has) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(&nitems, __popc(has));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (F) items[base + __popc(has & ((1u << lane) - 1u))] = (unsigned short)w;
+    }
+  }
+  __syncthreads();
+  const int n = nitems;
+  if (n == 0) return;  // empty tile (uniform)
+  // ---------------- 3. unions between runs of this tile (8-connectivity), thread per non-empty word
+  for (int it = tid; it < n; it += SEG_THREADS) {
+    const int w = items[it], wr = w / SEG_TW, wc = w % SEG_TW;
+    const uint32_t F = fsm[w];
+    const int sbase = w << SEG_LSPW;
+    if ((F & 1u) && wc > 0 && (fsm[w - 1] >> 31)) seg_lunion(sp, sbase, sbase - SEG_SPW + __popc(ssm[w - 1]) - 1);
+    if (wr == 0) continue;
+    const uint32_t al = wc > 0 ? fsm[w - SEG_TW - 1] : 0u, ac = fsm[w - SEG_TW], ar = wc < SEG_TW - 1 ? fsm[w - SEG_TW + 1] : 0u;
+    const uint32_t U = F & ac, UL = F & ((ac << 1) | (al >> 31)), UR = F & ((ac >> 1) | (ar << 31));
+    if (!(U | UL | UR)) continue;
+    const uint32_t Sa[3] = {wc > 0 ? ssm[w - SEG_TW - 1] : 0u, ssm[w - SEG_TW], wc < SEG_TW - 1 ? ssm[w - SEG_TW + 1] : 0u};
+    uint32_t S = ssm[w];
+    for (int j = 0; S; ++j) {
+      int s;
+      const uint32_t R = pcs_pop_run(F, S, s);
+      unsigned long long T = (((unsigned long long)(U & R)) << 1) | (unsigned long long)(UL & R) | (((unsigned long long)(UR & R)) << 2);
+      while (T) {
+        const int i = __ffsll((long long)T) - 1;
+        T &= T + (1ull << i);
+        const int rel = (i - 1) >> 5, ca = wc + rel;
+        if (ca >= 0 && ca < SEG_TW) {  // the run above lives in this tile
+          const uint32_t sa_w = Sa[rel + 1];
+          const int sa = pcs_start_at_or_below(sa_w, (i - 1) & 31);
+          seg_lunion(sp, sbase + j, ((w - SEG_TW + rel) << SEG_LSPW) + pcs_run_ord(sa_w, sa));
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---------------- 4. publish: every run points at the global id of its tile-local root; per-run intensity sums
+  const int NW = H * WW;
+  int* par = parent + b * ((long long)NW << SEG_LSPW);
+  int* rs = rsum + b * ((long long)NW << SEG_LSPW);
+  for (int it = tid; it < n; it += SEG_THREADS) {
+    const int w = items[it], wr = w / SEG_TW, wc = w % SEG_TW;
+    const int sbase = w << SEG_LSPW;
+    const int y = y0 + wr, kk = k0 + wc, gw = y * WW + kk;
+    const uint32_t F = fsm[w];
+    uint32_t S = ssm[w];
+    const uint16_t* px = src + (long long)y * W + (kk << 5);
+    const bool vec = (kk << 5) + 32 <= W && ((((uintptr_t)px) & 15) == 0);
+    uint32_t iw[16];
+    if (vec) {
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const uint4 q4 = __ldg(reinterpret_cast<const uint4*>(px) + v);
+        iw[4 * v] = q4.x;
+        iw[4 * v + 1] = q4.y;
+        iw[4 * v + 2] = q4.z;
+        iw[4 * v + 3] = q4.w;
+      }
+    }
+    for (int j = 0; S; ++j) {
+      int s;
+      const uint32_t R = pcs_pop_run(F, S, s);
+      const int root = seg_lfind(sp, sbase + j);
+      const int rw = root >> SEG_LSPW, rj = root & (SEG_SPW - 1);
+      par[j * NW + gw] = pcs_node<SEG_LSPW>((y0 + rw / SEG_TW) * WW + k0 + rw % SEG_TW, rj);
+      uint32_t sum = 0;  // <= 32 pixels of 16 bits: no overflow
+      if (vec) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const uint32_t p = (i & 1) ? (iw[i >> 1] >> 16) : (iw[i >> 1] & 0xffffu);
+          sum += (R >> i) & 1u ? p : 0u;
+        }
+      } else {
+        for (uint32_t m = R; m; m &= m - 1) sum += px[__ffs(m) - 1];
+      }
+      rs[j * NW + gw] = (int)sum;
+    }
+  }
+}
+
+// warp per 32-word chunk: roots get their raster-order rank (stored negated in the parent plane) and their table
+// row is initialised.  A root is the first raster pixel of its component, so the first-pixel column and the top
+// row of the bounding box are final here; the sums start at zero, the other bounds at their neutral values.
+__global__ void __launch_bounds__(256)
+    k_seg_rank_init(const uint32_t* __restrict__ bits, int* __restrict__ parent, const uint32_t* __restrict__ rootbits,
+                    const int* __restrict__ chunk, const int* __restrict__ offsets, long long* __restrict__ table, long long cap, int H, int W,
+                    int WW, int CPR) {
+  const int g32 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (g32 >= H * CPR) return;
+  const long long b = blockIdx.y;
+  const int ch = g32 % CPR, y = g32 / CPR;
+  const int k = ch * 32 + lane;
+  const long long wi = (b * H + y) * (long long)WW + k;
+  uint32_t roots = k < WW ? rootbits[wi] : 0u;  // bit j: the run of ordinal j is a root
+  const int cbase = chunk[b * (long long)H * CPR + g32];
+  int tot;
+  const int ex = pcs_warp_excl_scan(__popc(roots), lane, &tot);
+  if (!roots) return;
+  int rank = cbase + ex;
+  const int NW = H * WW;
+  int* par = parent + b * ((long long)NW << SEG_LSPW);
+  const int gw = y * WW + k;
+  const long long trow = offsets[b];
+  const uint32_t F = bits[wi];
+  uint32_t S = F & ~(F << 1);
+  for (int j = 0; S; ++j) {
+    const int s = __ffs(S) - 1;
+    S &= S - 1;
+    if (!((roots >> j) & 1u)) continue;
+    ++rank;
+    par[j * NW + gw] = -rank;
+    const long long row = trow + rank - 1;
+    if (row < cap) {
+      table[T_AREA * cap + row] = 0;
+      table[T_SUMY * cap + row] = 0;
+      table[T_SUMX * cap + row] = 0;
+      table[T_MINY * cap + row] = y;
+      table[T_MINX * cap + row] = 0x7fffffffffffffffLL;
+      table[T_MAXY * cap + row] = -1;
+      table[T_MAXX * cap + row] = -1;
+      table[T_FIRST * cap + row] = (long long)y * W + (k << 5) + s;
+      table[T_SUMI * cap + row] = 0;
+      table[T_OVERLAP * cap + row] = 0;
+    }
+  }
+}
+
+struct SegAcc {
+  int label;
+  int area, minx, maxx, maxy;
+  long long sx, sy, si;
+};
+
+__device__ __noinline__ void seg_flush(const SegAcc& a, long long* __restrict__ table, long long cap, long long base) {
+  if (a.label <= 0) return;
+  const long long row = base + a.label - 1;
+  if (row >= cap) return;
+  typedef unsigned long long ull;
+  atomicAdd((ull*)(table + T_AREA * cap + row), (ull)a.area);
+  atomicAdd((ull*)(table + T_SUMY * cap + row), (ull)a.sy);
+  atomicAdd((ull*)(table + T_SUMX * cap + row), (ull)a.sx);
+  atomicAdd((ull*)(table + T_SUMI * cap + row), (ull)a.si);
+  atomicMin(table + T_MINX * cap + row, (long long)a.minx);
+  atomicMax(table + T_MAXY * cap + row, (long long)a.maxy);
+  atomicMax(table + T_MAXX * cap + row, (long long)a.maxx);
+}
+
+// warp per (32-word chunk, strip of SEG_RROWS rows): labels out + per-label reductions.
+//  * a lane owns one word column and walks down the strip; the labels of its runs come from the parent plane (node
+//    -> root -> rank, two dependent loads, both L2 hits on the dense plane 0); the label of every run is written
+//    back (negated) so that the refine stage reads labels from that plane instead of the label image;
+//  * the row's 32 words are expanded to pixels with 16-byte stores, a lane writing 4 consecutive pixels: single-run
+//    words broadcast their label by shuffle, multi-run words go through shared memory;
+//  * the same lane accumulates area, coordinate sums, bbox and intensity (from the per-run sums k_seg_threshold_tile
+//    left) of the component it is walking through and reaches the table with 7 atomics only when the label under
+//    it changes: a blob crossing the strip costs one flush per column, not one per run.
+#define SEG_RROWS 8
+#define SEG_RL_WARPS 8
+template <typename OutT>
+__global__ void __launch_bounds__(SEG_RL_WARPS * 32)
+    k_seg_relabel_table(const uint32_t* __restrict__ bits, int* __restrict__ parent, const int* __restrict__ rsum,
+                        const int* __restrict__ offsets, long long* __restrict__ table, long long cap, OutT* __restrict__ out, int H, int W,
+                        int WW, int CPR, int strips) {
+  __shared__ int lab[SEG_RL_WARPS][32][33];
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // (strip, chunk) of the slice; the slice is blockIdx.y
+  const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+  if (g >= strips * CPR) return;
+  const long long b = blockIdx.y;
+  const int ch = g % CPR, strip = g / CPR;
+  const int k = ch * 32 + lane;
+  const int NW = H * WW;
+  int* par = parent + b * ((long long)NW << SEG_LSPW);
+  const int* rs = rsum + b * ((long long)NW << SEG_LSPW);
+  const long long tbase = offsets[b];
+  const int nk = min(32, WW - ch * 32);
+  const bool vec_out = sizeof(OutT) == 4 && (W & 3) == 0;
+  SegAcc acc;
+  acc.label = 0;
+  const int y0 = strip * SEG_RROWS;
+  const uint32_t* fcol = bits + (b * H + y0) * (long long)WW + k;
+  uint32_t fnext = k < WW ? __ldg(fcol) : 0u;
+#pragma unroll 1
+  for (int r = 0; r < SEG_RROWS; ++r) {
+    const int y = y0 + r;
+    if (y >= H) break;  // warp-uniform
+    const uint32_t F = fnext;
+    fnext = (k < WW && r + 1 < SEG_RROWS && y + 1 < H) ? __ldg(fcol + (long long)(r + 1) * WW) : 0u;
+    const uint32_t S = F & ~(F << 1);
+    const int gw = y * WW + k;
+    int one = 0;  // label of the word's only run
+    if (S) {
+      const int x0 = k << 5;
+      if (!(S & (S - 1))) {
+        const int p0 = par[gw];
+        one = p0 < 0 ? -p0 : -par[pcs_slot<SEG_LSPW>(p0, NW)];
+        if (p0 >= 0) par[gw] = -one;
+        const int s = __ffs(S) - 1, len = __popc(F), xs = x0 + s;
+        const int si = rs[gw];
+        if (one != acc.label) {
+          seg_flush(acc, table, cap, tbase);
+          acc.label = one;
+          acc.area = 0;
+          acc.sx = acc.sy = acc.si = 0;
+          acc.minx = xs;
+          acc.maxx = xs + len - 1;
+        }
+        acc.area += len;
+        acc.sx += (long long)len * xs + (long long)(len * (len - 1) / 2);
+        acc.sy += (long long)len * y;
+        acc.si += si;
+        acc.minx = min(acc.minx, xs);
+        acc.maxx = max(acc.maxx, xs + len - 1);
+        acc.maxy = y;
+      } else {
+        uint32_t rem = S;
+        for (int j = 0; rem; ++j) {
+          int s;
+          const uint32_t R = pcs_pop_run(F, rem, s);
+          const int p0 = par[j * NW + gw];
+          const int l = p0 < 0 ? -p0 : -par[pcs_slot<SEG_LSPW>(p0, NW)];
+          if (p0 >= 0) par[j * NW + gw] = -l;
+          lab[wl][lane][s] = l;
+          const int len = __popc(R), xs = x0 + s;
+          const int si = rs[j * NW + gw];
+          if (l != acc.label) {
+            seg_flush(acc, table, cap, tbase);
+            acc.label = l;
+            acc.area = 0;
+            acc.sx = acc.sy = acc.si = 0;
+            acc.minx = xs;
+            acc.maxx = xs + len - 1;
+          }
+          acc.area += len;
+          acc.sx += (long long)len * xs + (long long)(len * (len - 1) / 2);
+          acc.sy += (long long)len * y;
+          acc.si += si;
+          acc.minx = min(acc.minx, xs);
+          acc.maxx = max(acc.maxx, xs + len - 1);
+          acc.maxy = y;
+        }
+      }
+    }
+    __syncwarp();
+    OutT* orow = out + (b * H + y) * (long long)W;
+    if (vec_out) {
+      const int sub = lane >> 3, nib = (lane & 7) << 2;
+      const bool any = __ballot_sync(0xffffffffu, F != 0u) != 0u;
+      for (int k4 = 0; k4 < nk; k4 += 4) {
+        const int kk = k4 + sub;
+        int4 v = make_int4(0, 0, 0, 0);
+        if (any) {
+          const uint32_t f = __shfl_sync(0xffffffffu, F, kk & 31);
+          const uint32_t s = __shfl_sync(0xffffffffu, S, kk & 31);
+          const int l1 = __shfl_sync(0xffffffffu, one, kk & 31);
+          const uint32_t nb = kk < nk ? (f >> nib) & 0xfu : 0u;
+          if (nb) {
+            if (l1) {
+              v.x = (nb & 1u) ? l1 : 0;
+              v.y = (nb & 2u) ? l1 : 0;
+              v.z = (nb & 4u) ? l1 : 0;
+              v.w = (nb & 8u) ? l1 : 0;
+            } else {
+              if (nb & 1u) v.x = lab[wl][kk][pcs_start_at_or_below(s, nib)];
+              if (nb & 2u) v.y = lab[wl][kk][pcs_start_at_or_below(s, nib + 1)];
+              if (nb & 4u) v.z = lab[wl][kk][pcs_start_at_or_below(s, nib + 2)];
+              if (nb & 8u) v.w = lab[wl][kk][pcs_start_at_or_below(s, nib + 3)];
+            }
+          }
+        }
+        const int x = ((ch * 32 + kk) << 5) + nib;
+        if (kk < nk && x < W) *reinterpret_cast<int4*>(orow + x) = v;  // W % 4 == 0: x + 3 < W too
+      }
+    } else {
+      for (int kk = 0; kk < nk; ++kk) {
+        const uint32_t f = __shfl_sync(0xffffffffu, F, kk);
+        const uint32_t s = __shfl_sync(0xffffffffu, S, kk);
+        const int l1 = __shfl_sync(0xffffffffu, one, kk);
+        const int x = ((ch * 32 + kk) << 5) + lane;
+        int v = 0;
+        if ((f >> lane) & 1u) v = l1 ? l1 : lab[wl][kk][pcs_start_at_or_below(s, lane)];
+        if (x < W) orow[x] = (OutT)v;
+      }
+    }
+    __syncwarp();  // the next row reuses lab[wl]
+  }
+  seg_flush(acc, table, cap, tbase);
+}
+
+// ============================================================== host side
+int pcs_seg_threshold_tile(const uint16_t* img, const int32_t* thr, int median, uint32_t* bits, uint8_t* mask, int* parent, int* rsum,
+                           int B, int H, int W, cudaStream_t st) {
+  const int WW = pcs_words(W);
+  PCS_REQUIRE(B <= 65535 && (H + SEG_TR - 1) / SEG_TR <= 65535, "grid too large for the tile kernel");
+  dim3 gt((WW + SEG_TW - 1) / SEG_TW, (H + SEG_TR - 1) / SEG_TR, B);
+  if (median)
+    PCS_LAUNCH("k_seg_threshold_tile", st, (k_seg_threshold_tile<true><<<gt, SEG_THREADS, 0, st>>>(img, thr, bits, mask, parent, rsum, H, W, WW)));
+  else
+    PCS_LAUNCH("k_seg_threshold_tile", st, (k_seg_threshold_tile<false><<<gt, SEG_THREADS, 0, st>>>(img, thr, bits, mask, parent, rsum, H, W, WW)));
+  return pcs_check_launch("segment: threshold + median + tile labelling");
+}
+
+int pcs_seg_rank_relabel_table(const uint32_t* bits, const PcsCclWs& ws, const int* rsum, int64_t* table, int64_t cap, int32_t* labels,
+                               int B, int H, int W, cudaStream_t st) {
+  const int WW = pcs_words(W), CPR = (WW + 31) / 32;
+  dim3 gc(pcs_blocks((long long)H * CPR * 32, 256), B);
+  PCS_LAUNCH("k_seg_rank_init", st, (k_seg_rank_init<<<gc, 256, 0, st>>>(bits, ws.parent, ws.rootbits, ws.chunk, ws.offsets, (long long*)table, cap, H, W, WW, CPR)));
+  const int strips = (H + SEG_RROWS - 1) / SEG_RROWS;
+  dim3 gr(pcs_blocks((long long)strips * CPR * 32, SEG_RL_WARPS * 32), B);
+  PCS_LAUNCH("k_seg_relabel_table", st, (k_seg_relabel_table<int32_t><<<gr, SEG_RL_WARPS * 32, 0, st>>>(bits, ws.parent, rsum, ws.offsets, (long long*)table, cap, labels, H, W, WW, CPR, strips)));
+  return pcs_check_launch("segment: rank + relabel + table");
+}
