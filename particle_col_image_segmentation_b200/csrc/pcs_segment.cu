@@ -22,6 +22,9 @@
 #define SEG_TR 32  // tile rows   } the labeller's tile (pcs_ccl.cu: PcsTile<PcsBinProv>)
 #define SEG_TW 8   // tile words  }
 #define SEG_THREADS 128
+#ifndef SEG_MINBLOCKS
+#define SEG_MINBLOCKS 8
+#endif
 #define SEG_LSPW 4
 #define SEG_SPW 16
 #define SEG_RR (SEG_TR + 4)  // staged rows: two halo rows above and below
@@ -90,7 +93,7 @@ __device__ __forceinline__ uint32_t seg_cmp8(const uint4& q, uint32_t t) {
 //  4. per-run sums of the pixel values (the pixels come back from L1/L2: this CTA has just read them).
 // The memory-bound stage of one CTA overlaps the latency-bound union-find of its neighbours on the SM.
 template <bool MEDIAN>
-__global__ void __launch_bounds__(SEG_THREADS)
+__global__ void __launch_bounds__(SEG_THREADS, SEG_MINBLOCKS)
     k_seg_threshold_tile(const uint16_t* __restrict__ img, const int32_t* __restrict__ thr, uint32_t* __restrict__ bits,
                          uint8_t* __restrict__ mask, int* __restrict__ parent, int* __restrict__ rsum, int H, int W, int WW) {
   constexpr int NWORDS = SEG_TR * SEG_TW;
@@ -106,6 +109,7 @@ __global__ void __launch_bounds__(SEG_THREADS)
   const uint32_t t = (uint32_t)max(thr[b], 0);  // a negative threshold cannot occur (Otsu of uint16 data)
   if (tid == 0) nitems = 0;
   const int halo = MEDIAN ? 2 : 0;
+  const bool inner = k0 > 0 && ((k0 + SEG_TW) << 5) + 16 <= W;  // no word of this tile has a window beyond the row ends
   // ---------------- 1. stage the raw threshold bits
   const bool fast = x0 + 32 * SEG_TW <= W && (W & 7) == 0 && ((((uintptr_t)src) & 15) == 0);
   if (fast) {
@@ -168,7 +172,9 @@ __global__ void __launch_bounds__(SEG_THREADS)
         if (yi - 2 < H) {  // still needed by an output row of the image
           const int ry = pcs_reflect(yi, H);
           const uint32_t* rowp = &raw[ry - (y0 - 2)][1] - k0;  // rowp[k'] = word k' of that row
-          const unsigned long long win = pcs_window_reflect(rowp, k, W, WW, 2);
+          // words away from the left / right image border need no reflection: three shared loads and two funnel shifts
+          const unsigned long long win = inner ? ((unsigned long long)rowp[k] << 16) | (rowp[k - 1] >> 16) | ((unsigned long long)(rowp[k + 1] & 0xffffu) << 48)
+                                               : pcs_window_reflect(rowp, k, W, WW, 2);
           pcs_add5((uint32_t)(win >> 14), (uint32_t)(win >> 15), (uint32_t)(win >> 16), (uint32_t)(win >> 17), (uint32_t)(win >> 18), r0[i],
                    r1[i], r2[i]);
         }
@@ -275,10 +281,13 @@ __global__ void __launch_bounds__(SEG_THREADS)
       par[j * NW + gw] = pcs_node<SEG_LSPW>((y0 + rw / SEG_TW) * WW + k0 + rw % SEG_TW, rj);
       uint32_t sum = 0;  // <= 32 pixels of 16 bits: no overflow
       if (vec) {
+        // IDP.2A: two 16-bit pixels times two mask bytes (0 / 1) per instruction; the four mask bits of a nibble are
+        // spread to four bytes by one multiply (no carries: the shifted copies of a 4-bit value do not overlap)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const uint32_t p = (i & 1) ? (iw[i >> 1] >> 16) : (iw[i >> 1] & 0xffffu);
-          sum += (R >> i) & 1u ? p : 0u;
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t bm = (((R >> (4 * i)) & 0xfu) * 0x00204081u) & 0x01010101u;
+          sum = __dp2a_lo(iw[2 * i], bm, sum);
+          sum = __dp2a_hi(iw[2 * i + 1], bm, sum);
         }
       } else {
         for (uint32_t m = R; m; m &= m - 1) sum += px[__ffs(m) - 1];
@@ -357,16 +366,51 @@ __device__ __noinline__ void seg_flush(const SegAcc& a, long long* __restrict__ 
 }
 
 // warp per (32-word chunk, strip of SEG_RROWS rows): labels out + per-label reductions.
-//  * a lane owns one word column and walks down the strip; the labels of its runs come from the parent plane (node
-//    -> root -> rank, two dependent loads, both L2 hits on the dense plane 0); the label of every run is written
-//    back (negated) so that the refine stage reads labels from that plane instead of the label image;
-//  * the row's 32 words are expanded to pixels with 16-byte stores, a lane writing 4 consecutive pixels: single-run
-//    words broadcast their label by shuffle, multi-run words go through shared memory;
+//  * a lane owns one word column and walks down the strip.  The label of a run comes from the parent plane (node ->
+//    root -> rank: two dependent loads after the word itself, all L2 hits on the dense planes).  The three levels are
+//    software-pipelined over the rows -- while row r is expanded, the word of row r + 3, the parent / run sum of row
+//    r + 2 and the root rank of row r + 1 are in flight -- so the chain costs one round trip per strip, not three per
+//    row (stall samples of the unpipelined version: 40 % on that chain).  The label of every run is written back
+//    (negated) so that the refine stage reads labels from that plane instead of the label image;
+//  * a row's 32 words are expanded to pixels with 16-byte stores, a lane writing 4 consecutive pixels: single-run
+//    words broadcast their label by shuffle, words with several runs (4 % of the non-empty ones) go through a small
+//    shared table.  (Letting the owner lane of such a word write its 32 pixels itself looked cheaper and was not: one
+//    warp row in five holds such a word, and the whole warp then walks the per-pixel loop -- 157 vs 103 us per 16
+//    slices under ncu);
 //  * the same lane accumulates area, coordinate sums, bbox and intensity (from the per-run sums k_seg_threshold_tile
 //    left) of the component it is walking through and reaches the table with 7 atomics only when the label under
 //    it changes: a blob crossing the strip costs one flush per column, not one per run.
+#ifndef SEG_RROWS
 #define SEG_RROWS 8
-#define SEG_RL_WARPS 8
+#endif
+#ifndef SEG_RL_WARPS
+#define SEG_RL_WARPS 4
+#endif
+
+__device__ __forceinline__ void seg_acc_run(SegAcc& acc, int l, int len, int xs, int y, int si, long long* __restrict__ table,
+                                            long long cap, long long tbase) {
+  if (l != acc.label) {
+    seg_flush(acc, table, cap, tbase);
+    acc.label = l;
+    acc.area = 0;
+    acc.sx = acc.sy = acc.si = 0;
+    acc.minx = xs;
+    acc.maxx = xs + len - 1;
+  }
+  acc.area += len;
+  acc.sx += (long long)len * xs + (long long)(len * (len - 1) / 2);
+  acc.sy += (long long)len * y;
+  acc.si += si;
+  acc.minx = min(acc.minx, xs);
+  acc.maxx = max(acc.maxx, xs + len - 1);
+  acc.maxy = y;
+}
+
+__device__ __forceinline__ bool seg_single_run(uint32_t F) {
+  const uint32_t S = F & ~(F << 1);
+  return S != 0u && (S & (S - 1)) == 0u;
+}
+
 template <typename OutT>
 __global__ void __launch_bounds__(SEG_RL_WARPS * 32)
     k_seg_relabel_table(const uint32_t* __restrict__ bits, int* __restrict__ parent, const int* __restrict__ rsum,
@@ -385,44 +429,46 @@ __global__ void __launch_bounds__(SEG_RL_WARPS * 32)
   const long long tbase = offsets[b];
   const int nk = min(32, WW - ch * 32);
   const bool vec_out = sizeof(OutT) == 4 && (W & 3) == 0;
+  const int y0 = strip * SEG_RROWS;
+  const int yend = min(H, y0 + SEG_RROWS);
+  const int x0 = k << 5;
+  const uint32_t* fcol = bits + b * (long long)NW + k;
+  auto ldF = [&](int y) -> uint32_t { return (k < WW && y < yend) ? __ldg(fcol + (long long)y * WW) : 0u; };
+  // pipeline registers: F of rows y, y+1, y+2; parent / run sum of rows y, y+1; label of row y
+  uint32_t Fa = ldF(y0), Fb = ldF(y0 + 1), Fc = ldF(y0 + 2);
+  int pa = 0, sa = 0, pb = 0, sb = 0, oa = 0;
+  if (seg_single_run(Fa)) {
+    pa = par[y0 * WW + k];
+    sa = rs[y0 * WW + k];
+  }
+  if (seg_single_run(Fb)) {
+    pb = par[(y0 + 1) * WW + k];
+    sb = rs[(y0 + 1) * WW + k];
+  }
+  if (seg_single_run(Fa)) oa = pa < 0 ? -pa : -par[pcs_slot<SEG_LSPW>(pa, NW)];
   SegAcc acc;
   acc.label = 0;
-  const int y0 = strip * SEG_RROWS;
-  const uint32_t* fcol = bits + (b * H + y0) * (long long)WW + k;
-  uint32_t fnext = k < WW ? __ldg(fcol) : 0u;
 #pragma unroll 1
-  for (int r = 0; r < SEG_RROWS; ++r) {
-    const int y = y0 + r;
-    if (y >= H) break;  // warp-uniform
-    const uint32_t F = fnext;
-    fnext = (k < WW && r + 1 < SEG_RROWS && y + 1 < H) ? __ldg(fcol + (long long)(r + 1) * WW) : 0u;
+  for (int y = y0; y < yend; ++y) {
+    // issue the next levels
+    const uint32_t Fd = ldF(y + 3);
+    int pc = 0, sc = 0, ob = 0;
+    if (seg_single_run(Fc)) {
+      pc = par[(y + 2) * WW + k];
+      sc = rs[(y + 2) * WW + k];
+    }
+    if (seg_single_run(Fb)) ob = pb < 0 ? -pb : -par[pcs_slot<SEG_LSPW>(pb, NW)];
+    // row y
+    const uint32_t F = Fa;
     const uint32_t S = F & ~(F << 1);
+    const int one = oa;  // label of the word's only run (0: empty word or several runs)
     const int gw = y * WW + k;
-    int one = 0;  // label of the word's only run
+    OutT* orow = out + (b * H + y) * (long long)W;
     if (S) {
-      const int x0 = k << 5;
-      if (!(S & (S - 1))) {
-        const int p0 = par[gw];
-        one = p0 < 0 ? -p0 : -par[pcs_slot<SEG_LSPW>(p0, NW)];
-        if (p0 >= 0) par[gw] = -one;
-        const int s = __ffs(S) - 1, len = __popc(F), xs = x0 + s;
-        const int si = rs[gw];
-        if (one != acc.label) {
-          seg_flush(acc, table, cap, tbase);
-          acc.label = one;
-          acc.area = 0;
-          acc.sx = acc.sy = acc.si = 0;
-          acc.minx = xs;
-          acc.maxx = xs + len - 1;
-        }
-        acc.area += len;
-        acc.sx += (long long)len * xs + (long long)(len * (len - 1) / 2);
-        acc.sy += (long long)len * y;
-        acc.si += si;
-        acc.minx = min(acc.minx, xs);
-        acc.maxx = max(acc.maxx, xs + len - 1);
-        acc.maxy = y;
-      } else {
+      if (one) {
+        if (pa >= 0) par[gw] = -one;
+        seg_acc_run(acc, one, __popc(F), x0 + __ffs(S) - 1, y, sa, table, cap, tbase);
+      } else {  // several runs: their labels go through shared memory
         uint32_t rem = S;
         for (int j = 0; rem; ++j) {
           int s;
@@ -431,37 +477,19 @@ __global__ void __launch_bounds__(SEG_RL_WARPS * 32)
           const int l = p0 < 0 ? -p0 : -par[pcs_slot<SEG_LSPW>(p0, NW)];
           if (p0 >= 0) par[j * NW + gw] = -l;
           lab[wl][lane][s] = l;
-          const int len = __popc(R), xs = x0 + s;
-          const int si = rs[j * NW + gw];
-          if (l != acc.label) {
-            seg_flush(acc, table, cap, tbase);
-            acc.label = l;
-            acc.area = 0;
-            acc.sx = acc.sy = acc.si = 0;
-            acc.minx = xs;
-            acc.maxx = xs + len - 1;
-          }
-          acc.area += len;
-          acc.sx += (long long)len * xs + (long long)(len * (len - 1) / 2);
-          acc.sy += (long long)len * y;
-          acc.si += si;
-          acc.minx = min(acc.minx, xs);
-          acc.maxx = max(acc.maxx, xs + len - 1);
-          acc.maxy = y;
+          seg_acc_run(acc, l, __popc(R), x0 + s, y, rs[j * NW + gw], table, cap, tbase);
         }
       }
     }
     __syncwarp();
-    OutT* orow = out + (b * H + y) * (long long)W;
+    const bool any = __ballot_sync(0xffffffffu, F != 0u) != 0u;
     if (vec_out) {
       const int sub = lane >> 3, nib = (lane & 7) << 2;
-      const bool any = __ballot_sync(0xffffffffu, F != 0u) != 0u;
       for (int k4 = 0; k4 < nk; k4 += 4) {
         const int kk = k4 + sub;
         int4 v = make_int4(0, 0, 0, 0);
         if (any) {
           const uint32_t f = __shfl_sync(0xffffffffu, F, kk & 31);
-          const uint32_t s = __shfl_sync(0xffffffffu, S, kk & 31);
           const int l1 = __shfl_sync(0xffffffffu, one, kk & 31);
           const uint32_t nb = kk < nk ? (f >> nib) & 0xfu : 0u;
           if (nb) {
@@ -471,6 +499,7 @@ __global__ void __launch_bounds__(SEG_RL_WARPS * 32)
               v.z = (nb & 4u) ? l1 : 0;
               v.w = (nb & 8u) ? l1 : 0;
             } else {
+              const uint32_t s = f & ~(f << 1);
               if (nb & 1u) v.x = lab[wl][kk][pcs_start_at_or_below(s, nib)];
               if (nb & 2u) v.y = lab[wl][kk][pcs_start_at_or_below(s, nib + 1)];
               if (nb & 4u) v.z = lab[wl][kk][pcs_start_at_or_below(s, nib + 2)];
@@ -483,16 +512,24 @@ __global__ void __launch_bounds__(SEG_RL_WARPS * 32)
       }
     } else {
       for (int kk = 0; kk < nk; ++kk) {
-        const uint32_t f = __shfl_sync(0xffffffffu, F, kk);
-        const uint32_t s = __shfl_sync(0xffffffffu, S, kk);
-        const int l1 = __shfl_sync(0xffffffffu, one, kk);
+        const uint32_t f = any ? __shfl_sync(0xffffffffu, F, kk) : 0u;
+        const int l1 = any ? __shfl_sync(0xffffffffu, one, kk) : 0;
         const int x = ((ch * 32 + kk) << 5) + lane;
         int v = 0;
-        if ((f >> lane) & 1u) v = l1 ? l1 : lab[wl][kk][pcs_start_at_or_below(s, lane)];
+        if ((f >> lane) & 1u) v = l1 ? l1 : lab[wl][kk][pcs_start_at_or_below(f & ~(f << 1), lane)];
         if (x < W) orow[x] = (OutT)v;
       }
     }
     __syncwarp();  // the next row reuses lab[wl]
+    // rotate the pipeline
+    Fa = Fb;
+    Fb = Fc;
+    Fc = Fd;
+    pa = pb;
+    sa = sb;
+    pb = pc;
+    sb = sc;
+    oa = ob;
   }
   seg_flush(acc, table, cap, tbase);
 }
