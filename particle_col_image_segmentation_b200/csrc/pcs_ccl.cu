@@ -926,8 +926,7 @@ __global__ void __launch_bounds__(256)
 
 // ============================================================== host drivers
 template <class P>
-static int ccl_forest(const P& prov, int B, int conn, const PcsCclWs& ws, int32_t* counts, int zero_aux, cudaStream_t st,
-                      bool tiles_done = false) {
+static int ccl_forest(const P& prov, int B, int conn, const PcsCclWs& ws, int32_t* counts, int zero_aux, cudaStream_t st) {
   const int H = prov.H, WW = prov.WW;
   const int CPR = (WW + 31) / 32;
   dim3 gw(pcs_blocks((long long)H * WW, PCS_CCL_THREADS), B);
@@ -940,10 +939,10 @@ static int ccl_forest(const P& prov, int B, int conn, const PcsCclWs& ws, int32_
   const int per_slice = ntop * WW + (H - ntop) * 2 * ((WW + TW - 1) / TW);  // tile-edge words of one slice
   dim3 ge(pcs_blocks(per_slice, PCS_CCL_THREADS), B);
   if (conn == 8) {
-    if (!tiles_done) PCS_LAUNCH("k_ccl_tile", st, (k_ccl_tile<P, 8><<<gt, CCL_TILE_THREADS, 0, st>>>(prov, ws.parent)));
+    PCS_LAUNCH("k_ccl_tile", st, (k_ccl_tile<P, 8><<<gt, CCL_TILE_THREADS, 0, st>>>(prov, ws.parent)));
     PCS_LAUNCH("k_ccl_merge_edges", st, (k_ccl_merge_edges<P, 8><<<ge, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, B, per_slice)));
   } else {
-    if (!tiles_done) PCS_LAUNCH("k_ccl_tile", st, (k_ccl_tile<P, 4><<<gt, CCL_TILE_THREADS, 0, st>>>(prov, ws.parent)));
+    PCS_LAUNCH("k_ccl_tile", st, (k_ccl_tile<P, 4><<<gt, CCL_TILE_THREADS, 0, st>>>(prov, ws.parent)));
     PCS_LAUNCH("k_ccl_merge_edges", st, (k_ccl_merge_edges<P, 4><<<ge, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, B, per_slice)));
   }
   PCS_LAUNCH("k_ccl_flatten", st, k_ccl_flatten<P><<<dim3(pcs_blocks(((long long)H * CPR + 1) / 2 * 32, PCS_CCL_THREADS), B), PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, ws.rootbits, ws.chunk, zero_aux ? ws.aux : nullptr, B, CPR));
@@ -976,11 +975,11 @@ static int ccl_label(const P& prov, int B, int conn, void* labels, int label_byt
   return pcs_check_launch("ccl label");
 }
 
-// the passes after the tile-local one (tile-edge unions, flatten + root flags, per-slice counts and offsets) for a
-// binary mask whose tile pass has already run (k_seg_threshold_tile does it on the words it has just produced)
-int pcs_ccl_bin_forest_from_tiles(const uint32_t* bits, int B, int H, int W, const PcsCclWs& ws, int32_t* counts, cudaStream_t st) {
-  PcsBinProv prov{bits, H, W, pcs_words(W), 0};
-  return ccl_forest(prov, B, 8, ws, counts, 0, st, true);
+int pcs_ccl_scan_offsets(const PcsCclWs& ws, int32_t* counts, int B, int H, int W, cudaStream_t st) {
+  const int CPR = (pcs_words(W) + 31) / 32;
+  PCS_LAUNCH("k_ccl_scan", st, k_ccl_scan<<<B, 1024, 0, st>>>(ws.chunk, counts, H * CPR));
+  PCS_LAUNCH("k_ccl_offsets", st, k_ccl_offsets<<<1, 1024, 0, st>>>(counts, ws.offsets, B));
+  return pcs_check_launch("ccl scan");
 }
 
 static int check_dims(int B, int H, int W) {

@@ -173,8 +173,8 @@ size_t pcs_ccl_ws_bytes(int B, int H, int W, int with_aux);
 int pcs_ccl_ws_carve(void* ws, size_t ws_bytes, int B, int H, int W, int with_aux, PcsCclWs* out);
 
 // ---- pieces of the labeller the fused segment pipeline drives itself (pcs_segment.cu, pcs_pipeline.cu)
-int pcs_ccl_bin_forest_from_tiles(const uint32_t* bits, int B, int H, int W, const PcsCclWs& ws, int32_t* counts, cudaStream_t st);
-int pcs_seg_threshold_tile(const uint16_t* img, const int32_t* thr, int median, uint32_t* bits, uint8_t* mask, int* parent, int* rsum,
-                           int B, int H, int W, cudaStream_t st);
-int pcs_seg_rank_relabel_table(const uint32_t* bits, const PcsCclWs& ws, const int* rsum, int64_t* table, int64_t cap, int32_t* labels,
-                               int B, int H, int W, cudaStream_t st);
+// exclusive scan of ws.chunk per slice (in place), per-slice totals -> counts, exclusive scan of those -> ws.offsets
+int pcs_ccl_scan_offsets(const PcsCclWs& ws, int32_t* counts, int B, int H, int W, cudaStream_t st);
+int pcs_seg_label_stage(const uint16_t* img, const int32_t* thr, int median, uint32_t* bits, uint8_t* mask, int32_t* labels,
+                        int32_t* counts, int64_t* table, int64_t cap, const PcsCclWs& ws, int* rsum, int* wlist, int* wcount, int B, int H,
+                        int W, cudaStream_t st);

@@ -16,7 +16,9 @@ struct SegWs {
   size_t ccl_bytes;
   void* edt;
   size_t edt_bytes;
-  int* rsum;  // per-run intensity sums, laid out like the labeller's parent planes
+  int* rsum;    // per-run intensity sums, laid out like the labeller's parent planes
+  int* wlist;   // per slice: the non-empty words (slice-local word indices)
+  int* wcount;  // per slice: how many
 };
 
 size_t seg_carve(void* ws, int B, int H, int W, SegWs* out) {
@@ -39,6 +41,8 @@ size_t seg_carve(void* ws, int B, int H, int W, SegWs* out) {
   w.edt_bytes = pcs_edt_workspace_bytes(B, H, W);
   w.edt = take(w.edt_bytes);
   w.rsum = (int*)take((size_t)B * H * pcs_words(W) * 16 * 4);
+  w.wlist = (int*)take((size_t)B * H * pcs_words(W) * 4);
+  w.wcount = (int*)take((size_t)B * 4);
   if (out) *out = w;
   return n;
 }
@@ -73,9 +77,7 @@ int pcs_segment_chunk(const uint16_t* img, int B, int H, int W, int denoise_size
     PcsCclWs cw;
     STEP(pcs_ccl_ws_carve(w.ccl, w.ccl_bytes, B, H, W, 0, &cw));
     bits = w.bits;
-    STEP(pcs_seg_threshold_tile(img, thr, denoise_size == 5, w.bits, mask, cw.parent, w.rsum, B, H, W, st));
-    STEP(pcs_ccl_bin_forest_from_tiles(w.bits, B, H, W, cw, counts, st));
-    STEP(pcs_seg_rank_relabel_table(w.bits, cw, w.rsum, table, cap, labels, B, H, W, st));
+    STEP(pcs_seg_label_stage(img, thr, denoise_size == 5, w.bits, mask, labels, counts, table, cap, cw, w.rsum, w.wlist, w.wcount, B, H, W, st));
     cudaMemcpyAsync(offsets, cw.offsets, (size_t)(B + 1) * 4, cudaMemcpyDeviceToDevice, st);
   } else {
     STEP(pcs_compare_u16(img, 0, thr, 0, w.raw, nullptr, B, H, W, stream));

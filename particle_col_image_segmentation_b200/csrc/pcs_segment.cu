@@ -95,8 +95,10 @@ __device__ __forceinline__ uint32_t seg_cmp8(const uint4& q, uint32_t t) {
 template <bool MEDIAN>
 __global__ void __launch_bounds__(SEG_THREADS, SEG_MINBLOCKS)
     k_seg_threshold_tile(const uint16_t* __restrict__ img, const int32_t* __restrict__ thr, uint32_t* __restrict__ bits,
-                         uint8_t* __restrict__ mask, int* __restrict__ parent, int* __restrict__ rsum, int H, int W, int WW) {
+                         uint8_t* __restrict__ mask, int* __restrict__ parent, int* __restrict__ rsum, int* __restrict__ wlist,
+                         int* __restrict__ wcount, int H, int W, int WW) {
   constexpr int NWORDS = SEG_TR * SEG_TW;
+  __shared__ int s_lbase;
   __shared__ uint32_t raw[SEG_RR][SEG_RW];
   __shared__ int sp[NWORDS * SEG_SPW];
   __shared__ uint32_t fsm[NWORDS], ssm[NWORDS];
@@ -221,6 +223,9 @@ __global__ void __launch_bounds__(SEG_THREADS, SEG_MINBLOCKS)
   __syncthreads();
   const int n = nitems;
   if (n == 0) return;  // empty tile (uniform)
+  // the slice's list of non-empty words: the sparse passes that follow (tile-edge unions, flatten, ranking) walk this
+  // list instead of all words -- four words in five are empty
+  if (tid == 0) s_lbase = atomicAdd(wcount + b, n);
   // ---------------- 3. unions between runs of this tile (8-connectivity), thread per non-empty word
   for (int it = tid; it < n; it += SEG_THREADS) {
     const int w = items[it], wr = w / SEG_TW, wc = w % SEG_TW;
@@ -254,10 +259,12 @@ __global__ void __launch_bounds__(SEG_THREADS, SEG_MINBLOCKS)
   const int NW = H * WW;
   int* par = parent + b * ((long long)NW << SEG_LSPW);
   int* rs = rsum + b * ((long long)NW << SEG_LSPW);
+  int* wl = wlist + b * (long long)NW + s_lbase;
   for (int it = tid; it < n; it += SEG_THREADS) {
     const int w = items[it], wr = w / SEG_TW, wc = w % SEG_TW;
     const int sbase = w << SEG_LSPW;
     const int y = y0 + wr, kk = k0 + wc, gw = y * WW + kk;
+    wl[it] = gw;
     const uint32_t F = fsm[w];
     uint32_t S = ssm[w];
     const uint16_t* px = src + (long long)y * W + (kk << 5);
@@ -297,50 +304,136 @@ __global__ void __launch_bounds__(SEG_THREADS, SEG_MINBLOCKS)
   }
 }
 
-// warp per 32-word chunk: roots get their raster-order rank (stored negated in the parent plane) and their table
-// row is initialised.  A root is the first raster pixel of its component, so the first-pixel column and the top
-// row of the bounding box are final here; the sums start at zero, the other bounds at their neutral values.
-__global__ void __launch_bounds__(256)
-    k_seg_rank_init(const uint32_t* __restrict__ bits, int* __restrict__ parent, const uint32_t* __restrict__ rootbits,
-                    const int* __restrict__ chunk, const int* __restrict__ offsets, long long* __restrict__ table, long long cap, int H, int W,
-                    int WW, int CPR) {
-  const int g32 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (g32 >= H * CPR) return;
+// ---------------------------------------------------------------- sparse passes over the list of non-empty words
+// grid = (GX, B); thread per listed word (grid-stride), the slice's count is read from device memory.
+#define SEG_LIST_THREADS 256
+
+// the unions k_seg_threshold_tile could not do: adjacencies across a tile edge (top row of a tile: everything above;
+// first / last word column: the run to the left and the diagonal neighbours beyond the column)
+__global__ void __launch_bounds__(SEG_LIST_THREADS)
+    k_seg_merge_list(const uint32_t* __restrict__ bits, int* __restrict__ parent, const int* __restrict__ wlist,
+                     const int* __restrict__ wcount, int H, int W, int WW) {
   const long long b = blockIdx.y;
-  const int ch = g32 % CPR, y = g32 / CPR;
-  const int k = ch * 32 + lane;
-  const long long wi = (b * H + y) * (long long)WW + k;
-  uint32_t roots = k < WW ? rootbits[wi] : 0u;  // bit j: the run of ordinal j is a root
-  const int cbase = chunk[b * (long long)H * CPR + g32];
-  int tot;
-  const int ex = pcs_warp_excl_scan(__popc(roots), lane, &tot);
-  if (!roots) return;
-  int rank = cbase + ex;
   const int NW = H * WW;
+  const int n = min(wcount[b], NW);
+  const uint32_t* bb = bits + b * (long long)NW;
   int* par = parent + b * ((long long)NW << SEG_LSPW);
-  const int gw = y * WW + k;
+  const int* wl = wlist + b * (long long)NW;
+  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < n; it += gridDim.x * blockDim.x) {
+    const int gw = wl[it], y = gw / WW, k = gw - y * WW;
+    const bool top = (y % SEG_TR) == 0, left = (k % SEG_TW) == 0, right = (k % SEG_TW) == SEG_TW - 1;
+    if (!(top || left || right)) continue;
+    const uint32_t F = __ldg(bb + gw);
+    if (left && k > 0 && (F & 1u)) {
+      const uint32_t Fl = __ldg(bb + gw - 1);
+      if (Fl >> 31) pcs_uf_union<SEG_LSPW>(par, NW, pcs_node<SEG_LSPW>(gw, 0), pcs_node<SEG_LSPW>(gw - 1, __popc(Fl & ~(Fl << 1)) - 1));
+    }
+    if (y == 0) continue;
+    const uint32_t al = k > 0 ? __ldg(bb + gw - WW - 1) : 0u, ac = __ldg(bb + gw - WW), ar = k + 1 < WW ? __ldg(bb + gw - WW + 1) : 0u;
+    const uint32_t U = F & ac, UL = F & ((ac << 1) | (al >> 31)), UR = F & ((ac >> 1) | (ar << 31));
+    if (!(U | UL | UR)) continue;
+    const uint32_t Sa[3] = {al & ~(al << 1), ac & ~(ac << 1), ar & ~(ar << 1)};
+    uint32_t S = F & ~(F << 1);
+    for (int j = 0; S; ++j) {
+      int s;
+      const uint32_t R = pcs_pop_run(F, S, s);
+      unsigned long long T = (((unsigned long long)(U & R)) << 1) | (unsigned long long)(UL & R) | (((unsigned long long)(UR & R)) << 2);
+      while (T) {
+        const int i = __ffsll((long long)T) - 1;
+        T &= T + (1ull << i);
+        const int rel = (i - 1) >> 5;
+        if (!(top || (rel < 0 && left) || (rel > 0 && right))) continue;  // done inside the tile
+        const uint32_t sa_w = Sa[rel + 1];
+        const int sa = pcs_start_at_or_below(sa_w, (i - 1) & 31);
+        pcs_uf_union<SEG_LSPW>(par, NW, pcs_node<SEG_LSPW>(gw, j), pcs_node<SEG_LSPW>(gw - WW + rel, pcs_run_ord(sa_w, sa)));
+      }
+    }
+  }
+}
+
+// every run points at its root; root flags per word (bit j: the run of ordinal j is a root); roots per 32-word chunk
+// (rootbits and chunk are zeroed beforehand: only listed words are written)
+__global__ void __launch_bounds__(SEG_LIST_THREADS)
+    k_seg_flatten_list(const uint32_t* __restrict__ bits, int* __restrict__ parent, const int* __restrict__ wlist,
+                       const int* __restrict__ wcount, uint32_t* __restrict__ rootbits, int* __restrict__ chunk, int H, int W, int WW,
+                       int CPR) {
+  const long long b = blockIdx.y;
+  const int NW = H * WW;
+  const int n = min(wcount[b], NW);
+  const uint32_t* bb = bits + b * (long long)NW;
+  int* par = parent + b * ((long long)NW << SEG_LSPW);
+  const int* wl = wlist + b * (long long)NW;
+  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < n; it += gridDim.x * blockDim.x) {
+    const int gw = wl[it];
+    const uint32_t F = __ldg(bb + gw);
+    const int nr = __popc(F & ~(F << 1));
+    uint32_t roots = 0;
+    for (int j = 0; j < nr; ++j) {
+      const int nd = pcs_node<SEG_LSPW>(gw, j);
+      int r = nd, q = pcs_ld_cg(par + j * NW + gw);
+      const int first = q;
+      while (q != r) {
+        r = q;
+        q = pcs_ld_cg(par + pcs_slot<SEG_LSPW>(r, NW));
+      }
+      if (r == nd)
+        roots |= 1u << j;
+      else if (first != r)
+        par[j * NW + gw] = r;
+    }
+    rootbits[b * (long long)NW + gw] = roots;
+    if (roots) {
+      const int y = gw / WW, k = gw - y * WW;
+      atomicAdd(chunk + b * (long long)H * CPR + y * CPR + (k >> 5), __popc(roots));
+    }
+  }
+}
+
+// roots get their raster-order rank (stored negated in the parent plane) and their table row is initialised.  The
+// rank of a root = roots of the slice before its 32-word chunk (scanned chunk counts) + roots in the chunk's earlier
+// words + its ordinal among the roots of its own word.  A root is the first raster pixel of its component, so the
+// first-pixel column and the top row of the bounding box are final here; the sums start at zero, the other bounds
+// at their neutral values.
+__global__ void __launch_bounds__(SEG_LIST_THREADS)
+    k_seg_rank_list(const uint32_t* __restrict__ bits, int* __restrict__ parent, const int* __restrict__ wlist,
+                    const int* __restrict__ wcount, const uint32_t* __restrict__ rootbits, const int* __restrict__ chunk,
+                    const int* __restrict__ offsets, long long* __restrict__ table, long long cap, int H, int W, int WW, int CPR) {
+  const long long b = blockIdx.y;
+  const int NW = H * WW;
+  const int n = min(wcount[b], NW);
+  const uint32_t* bb = bits + b * (long long)NW;
+  const uint32_t* rb = rootbits + b * (long long)NW;
+  int* par = parent + b * ((long long)NW << SEG_LSPW);
+  const int* wl = wlist + b * (long long)NW;
   const long long trow = offsets[b];
-  const uint32_t F = bits[wi];
-  uint32_t S = F & ~(F << 1);
-  for (int j = 0; S; ++j) {
-    const int s = __ffs(S) - 1;
-    S &= S - 1;
-    if (!((roots >> j) & 1u)) continue;
-    ++rank;
-    par[j * NW + gw] = -rank;
-    const long long row = trow + rank - 1;
-    if (row < cap) {
-      table[T_AREA * cap + row] = 0;
-      table[T_SUMY * cap + row] = 0;
-      table[T_SUMX * cap + row] = 0;
-      table[T_MINY * cap + row] = y;
-      table[T_MINX * cap + row] = 0x7fffffffffffffffLL;
-      table[T_MAXY * cap + row] = -1;
-      table[T_MAXX * cap + row] = -1;
-      table[T_FIRST * cap + row] = (long long)y * W + (k << 5) + s;
-      table[T_SUMI * cap + row] = 0;
-      table[T_OVERLAP * cap + row] = 0;
+  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < n; it += gridDim.x * blockDim.x) {
+    const int gw = wl[it];
+    const uint32_t roots = rb[gw];
+    if (!roots) continue;
+    const int y = gw / WW, k = gw - y * WW;
+    int rank = chunk[b * (long long)H * CPR + y * CPR + (k >> 5)];
+    for (int w = gw - (k & 31); w < gw; ++w) rank += __popc(__ldg(rb + w));
+    const uint32_t F = __ldg(bb + gw);
+    uint32_t S = F & ~(F << 1);
+    for (int j = 0; S; ++j) {
+      const int s = __ffs(S) - 1;
+      S &= S - 1;
+      if (!((roots >> j) & 1u)) continue;
+      ++rank;
+      par[j * NW + gw] = -rank;
+      const long long row = trow + rank - 1;
+      if (row < cap) {
+        table[T_AREA * cap + row] = 0;
+        table[T_SUMY * cap + row] = 0;
+        table[T_SUMX * cap + row] = 0;
+        table[T_MINY * cap + row] = y;
+        table[T_MINX * cap + row] = 0x7fffffffffffffffLL;
+        table[T_MAXY * cap + row] = -1;
+        table[T_MAXX * cap + row] = -1;
+        table[T_FIRST * cap + row] = (long long)y * W + (k << 5) + s;
+        table[T_SUMI * cap + row] = 0;
+        table[T_OVERLAP * cap + row] = 0;
+      }
     }
   }
 }
@@ -535,25 +628,33 @@ __global__ void __launch_bounds__(SEG_RL_WARPS * 32)
 }
 
 // ============================================================== host side
-int pcs_seg_threshold_tile(const uint16_t* img, const int32_t* thr, int median, uint32_t* bits, uint8_t* mask, int* parent, int* rsum,
-                           int B, int H, int W, cudaStream_t st) {
-  const int WW = pcs_words(W);
+// The labelling stage of the pipeline: img, thr -> bits, uint8 mask, int32 labels, counts, offsets, region table.
+int pcs_seg_label_stage(const uint16_t* img, const int32_t* thr, int median, uint32_t* bits, uint8_t* mask, int32_t* labels,
+                        int32_t* counts, int64_t* table, int64_t cap, const PcsCclWs& ws, int* rsum, int* wlist, int* wcount, int B, int H,
+                        int W, cudaStream_t st) {
+  const int WW = pcs_words(W), CPR = (WW + 31) / 32;
+  const long long NW = (long long)H * WW;
   PCS_REQUIRE(B <= 65535 && (H + SEG_TR - 1) / SEG_TR <= 65535, "grid too large for the tile kernel");
+  cudaMemsetAsync(wcount, 0, (size_t)B * 4, st);
+  cudaMemsetAsync(ws.rootbits, 0, (size_t)B * NW * 4, st);
+  cudaMemsetAsync(ws.chunk, 0, (size_t)B * H * CPR * 4, st);
   dim3 gt((WW + SEG_TW - 1) / SEG_TW, (H + SEG_TR - 1) / SEG_TR, B);
   if (median)
-    PCS_LAUNCH("k_seg_threshold_tile", st, (k_seg_threshold_tile<true><<<gt, SEG_THREADS, 0, st>>>(img, thr, bits, mask, parent, rsum, H, W, WW)));
+    PCS_LAUNCH("k_seg_threshold_tile", st, (k_seg_threshold_tile<true><<<gt, SEG_THREADS, 0, st>>>(img, thr, bits, mask, ws.parent, rsum, wlist, wcount, H, W, WW)));
   else
-    PCS_LAUNCH("k_seg_threshold_tile", st, (k_seg_threshold_tile<false><<<gt, SEG_THREADS, 0, st>>>(img, thr, bits, mask, parent, rsum, H, W, WW)));
-  return pcs_check_launch("segment: threshold + median + tile labelling");
-}
-
-int pcs_seg_rank_relabel_table(const uint32_t* bits, const PcsCclWs& ws, const int* rsum, int64_t* table, int64_t cap, int32_t* labels,
-                               int B, int H, int W, cudaStream_t st) {
-  const int WW = pcs_words(W), CPR = (WW + 31) / 32;
-  dim3 gc(pcs_blocks((long long)H * CPR * 32, 256), B);
-  PCS_LAUNCH("k_seg_rank_init", st, (k_seg_rank_init<<<gc, 256, 0, st>>>(bits, ws.parent, ws.rootbits, ws.chunk, ws.offsets, (long long*)table, cap, H, W, WW, CPR)));
+    PCS_LAUNCH("k_seg_threshold_tile", st, (k_seg_threshold_tile<false><<<gt, SEG_THREADS, 0, st>>>(img, thr, bits, mask, ws.parent, rsum, wlist, wcount, H, W, WW)));
+  // list passes: about one thread per listed word on blob-like masks (a fifth of the words), grid-stride beyond that
+  long long gx = (NW / 5 + SEG_LIST_THREADS - 1) / SEG_LIST_THREADS;
+  if (gx < 1) gx = 1;
+  if (gx > 1024) gx = 1024;
+  dim3 gl((unsigned)gx, B);
+  PCS_LAUNCH("k_seg_merge_list", st, (k_seg_merge_list<<<gl, SEG_LIST_THREADS, 0, st>>>(bits, ws.parent, wlist, wcount, H, W, WW)));
+  PCS_LAUNCH("k_seg_flatten_list", st, (k_seg_flatten_list<<<gl, SEG_LIST_THREADS, 0, st>>>(bits, ws.parent, wlist, wcount, ws.rootbits, ws.chunk, H, W, WW, CPR)));
+  int rc = pcs_ccl_scan_offsets(ws, counts, B, H, W, st);
+  if (rc) return rc;
+  PCS_LAUNCH("k_seg_rank_list", st, (k_seg_rank_list<<<gl, SEG_LIST_THREADS, 0, st>>>(bits, ws.parent, wlist, wcount, ws.rootbits, ws.chunk, ws.offsets, (long long*)table, cap, H, W, WW, CPR)));
   const int strips = (H + SEG_RROWS - 1) / SEG_RROWS;
   dim3 gr(pcs_blocks((long long)strips * CPR * 32, SEG_RL_WARPS * 32), B);
   PCS_LAUNCH("k_seg_relabel_table", st, (k_seg_relabel_table<int32_t><<<gr, SEG_RL_WARPS * 32, 0, st>>>(bits, ws.parent, rsum, ws.offsets, (long long*)table, cap, labels, H, W, WW, CPR, strips)));
-  return pcs_check_launch("segment: rank + relabel + table");
+  return pcs_check_launch("segment: labelling stage");
 }
