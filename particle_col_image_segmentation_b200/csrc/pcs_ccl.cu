@@ -792,10 +792,23 @@ __device__ __forceinline__ void refine_paint(uint32_t* cb, int* diff, int a, int
   }
 }
 
+// PLANES = false: run labels are read from the int32 label image (the drop-in primitive).
+// PLANES = true (the pipeline): run labels are read, negated, from the labeller's parent planes, where
+// k_seg_relabel_table left them -- a coalesced load of the dense plane 0 for every word with one run instead of a
+// scattered 4-byte read of a 16 MiB label image; candidate words are appended to the slice's list and their runs get
+// fresh singleton parents in `hpar`, so the hole stage that follows only walks that list.
+struct PcsRefineSparse {
+  const int* labpar;  // parent planes holding -label for every run
+  int* hpar;          // parent planes of the hole forest
+  int* clist;         // per slice: candidate words
+  int* ccount;        // per slice: how many
+};
+
+template <bool PLANES>
 __global__ void __launch_bounds__(REFINE_MAX_WARPS * 32)
     k_refine_rows(const uint32_t* __restrict__ fg, const int32_t* __restrict__ labels, const long long* __restrict__ table,
                   long long cap, const int* __restrict__ offsets, long long min_size, uint32_t* __restrict__ kept_out,
-                  uint32_t* __restrict__ cand_out, long long rows, int H, int W, int WW) {
+                  uint32_t* __restrict__ cand_out, long long rows, int H, int W, int WW, PcsRefineSparse sp) {
   extern __shared__ uint32_t sm[];
   const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + wl;
@@ -811,8 +824,11 @@ __global__ void __launch_bounds__(REFINE_MAX_WARPS * 32)
   }
   if (lane == 0) diff[WW] = 0;
   const long long b = row / H;
+  const int y = (int)(row - b * H);
+  const int NW = H * WW;
   const long long tbase = offsets ? (long long)offsets[b] : 0;
-  const int32_t* lrow = labels + row * (long long)W;
+  const int32_t* lrow = PLANES ? nullptr : labels + row * (long long)W;
+  const int* lpl = PLANES ? sp.labpar + b * ((long long)NW << 4) + (long long)y * WW : nullptr;  // plane j of word k: lpl[j * NW + k]
   const uint32_t* frow = fg + row * (long long)WW;
   int n = 0;
   bool overflow = false;
@@ -825,12 +841,12 @@ __global__ void __launch_bounds__(REFINE_MAX_WARPS * 32)
       kept = 0u;
       cnt = 0;
       uint32_t S = f & ~(f << 1);
-      while (S) {
+      for (int j = 0; S; ++j) {
         const int s = __ffs(S) - 1;
         S &= S - 1;
         const uint32_t upper = ~(f >> s);
         const int len = upper ? (__ffs(upper) - 1) : 32;
-        const long long r = tbase + __ldg(lrow + (k << 5) + s) - 1;
+        const long long r = tbase + (PLANES ? -lpl[j * NW + k] : __ldg(lrow + (k << 5) + s)) - 1;
         if (r < 0 || r >= cap || __ldg(table + r) < min_size) continue;  // column 0 of the table: area
         kept |= (len >= 32 ? 0xffffffffu : ((1u << len) - 1u)) << s;
         ++cnt;
@@ -842,13 +858,14 @@ __global__ void __launch_bounds__(REFINE_MAX_WARPS * 32)
     overflow |= n > REFINE_RMAX;
     if (!overflow) {
       uint32_t S = kept & ~(kept << 1);
+      const uint32_t Sf = f & ~(f << 1);  // the ordinal of a kept run counts the dropped runs of the word too
       while (S) {  // labels come back from L1 this time
         const int s = __ffs(S) - 1;
         S &= S - 1;
         const uint32_t upper = ~(kept >> s);
         const int len = upper ? (__ffs(upper) - 1) : 32;
         const uint32_t xs = (uint32_t)((k << 5) + s);
-        rl[at] = __ldg(lrow + xs);
+        rl[at] = PLANES ? -lpl[pcs_run_ord(Sf, s) * NW + k] : __ldg(lrow + xs);
         rse[at] = xs | ((xs + len - 1) << 16);
         ++at;
       }
@@ -859,8 +876,31 @@ __global__ void __launch_bounds__(REFINE_MAX_WARPS * 32)
     }
   }
   __syncwarp();
+  // a candidate word leaves for the plane and, in the pipeline, for the slice's list with singleton parents
+  auto emit = [&](int k, uint32_t c) {
+    if (k < WW) cand_out[row * (long long)WW + k] = c;
+    if (PLANES) {
+      const unsigned has = __ballot_sync(0xffffffffu, k < WW && c != 0u);
+      if (has) {
+        const int leader = __ffs(has) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(sp.ccount + b, __popc(has));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (k < WW && c != 0u) {
+          const int gw = y * WW + k;
+          sp.clist[b * (long long)NW + base + __popc(has & ((1u << lane) - 1u))] = gw;
+          int* hp = sp.hpar + b * ((long long)NW << 4);
+          const int nr = __popc(c & ~(c << 1));
+          for (int j = 0; j < nr; ++j) hp[j * NW + gw] = pcs_node<4>(gw, j);
+        }
+      }
+    }
+  };
   if (overflow) {
-    for (int k = lane; k < WW; k += 32) cand_out[row * (long long)WW + k] = ~kw[k] & pcs_valid_mask(k, W);
+    for (int k0 = 0; k0 < WW; k0 += 32) {
+      const int k = k0 + lane;
+      emit(k, k < WW ? ~kw[k] & pcs_valid_mask(k, W) : 0u);
+    }
     return;
   }
   int fb = -1;  // end of the row prefix painted when a search window ran out
@@ -887,7 +927,119 @@ __global__ void __launch_bounds__(REFINE_MAX_WARPS * 32)
     int tot;
     const int cov = carry + pcs_warp_excl_scan(d, lane, &tot) + d;
     carry += tot;
-    if (k < WW) cand_out[row * (long long)WW + k] = (cb[k] | (cov > 0 ? 0xffffffffu : 0u)) & ~kw[k] & pcs_valid_mask(k, W);
+    emit(k, k < WW ? (cb[k] | (cov > 0 ? 0xffffffffu : 0u)) & ~kw[k] & pcs_valid_mask(k, W) : 0u);
+  }
+}
+
+// ---------------------------------------------------------------- hole stage over the candidate list (pipeline)
+// grid = (GX, B), thread per listed candidate word (grid-stride).  Candidates are few (blob-like masks have next to
+// none), so the three passes below cost a launch each instead of the five dense passes of the generic path.
+#define HOLE_LIST_THREADS 128
+
+// 4-connected unions between candidate runs: with the word to the left and with the row above
+__global__ void __launch_bounds__(HOLE_LIST_THREADS)
+    k_hole_union_list(const uint32_t* __restrict__ cand, int* __restrict__ hpar, const int* __restrict__ clist,
+                      const int* __restrict__ ccount, int H, int WW) {
+  const long long b = blockIdx.y;
+  const int NW = H * WW;
+  const int n = min(ccount[b], NW);
+  const uint32_t* cc = cand + b * (long long)NW;
+  int* par = hpar + b * ((long long)NW << 4);
+  const int* cl = clist + b * (long long)NW;
+  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < n; it += gridDim.x * blockDim.x) {
+    const int gw = cl[it], y = gw / WW, k = gw - y * WW;
+    const uint32_t C = __ldg(cc + gw);
+    if (k > 0 && (C & 1u)) {
+      const uint32_t Cl = __ldg(cc + gw - 1);
+      if (Cl >> 31) pcs_uf_union<4>(par, NW, pcs_node<4>(gw, 0), pcs_node<4>(gw - 1, __popc(Cl & ~(Cl << 1)) - 1));
+    }
+    if (y == 0) continue;
+    const uint32_t ac = __ldg(cc + gw - WW);
+    if (!(C & ac)) continue;
+    const uint32_t Sa = ac & ~(ac << 1);
+    uint32_t S = C & ~(C << 1);
+    for (int j = 0; S; ++j) {
+      int s;
+      const uint32_t R = pcs_pop_run(C, S, s);
+      unsigned long long T = (unsigned long long)(R & ac);  // every stretch of set bits lies in one run of the row above
+      while (T) {
+        const int i = __ffsll((long long)T) - 1;
+        T &= T + (1ull << i);
+        pcs_uf_union<4>(par, NW, pcs_node<4>(gw, j), pcs_node<4>(gw - WW, pcs_run_ord(Sa, pcs_start_at_or_below(Sa, i))));
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ int pcs_hole_root(const int* par, int NW, int n) {  // root id of n; roots may carry PCS_MARK
+  int r = n;
+  while (true) {
+    const int p = pcs_ld_cg(par + pcs_slot<4>(r, NW));
+    if (p < 0 || p == r) return r;
+    r = p;
+  }
+}
+
+// candidate runs that touch the image border or background outside the candidate set are open: mark their roots
+__global__ void __launch_bounds__(HOLE_LIST_THREADS)
+    k_hole_mark_list(const uint32_t* __restrict__ kept, const uint32_t* __restrict__ cand, int* __restrict__ hpar,
+                     const int* __restrict__ clist, const int* __restrict__ ccount, int H, int W, int WW) {
+  const long long b = blockIdx.y;
+  const int NW = H * WW;
+  const int n = min(ccount[b], NW);
+  const uint32_t* kk = kept + b * (long long)NW;
+  const uint32_t* cc = cand + b * (long long)NW;
+  int* par = hpar + b * ((long long)NW << 4);
+  const int* cl = clist + b * (long long)NW;
+  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < n; it += gridDim.x * blockDim.x) {
+    const int gw = cl[it], y = gw / WW, k = gw - y * WW;
+    const uint32_t C = __ldg(cc + gw);
+    auto open_at = [&](int w, int kw) { return ~__ldg(kk + w) & ~__ldg(cc + w) & pcs_valid_mask(kw, W); };
+    const uint32_t n_c = open_at(gw, k);
+    uint32_t adj = (n_c << 1) | (n_c >> 1);
+    adj |= (k > 0) ? (open_at(gw - 1, k - 1) >> 31) : 1u;
+    if (k + 1 < WW) adj |= open_at(gw + 1, k + 1) << 31;
+    adj |= (y > 0) ? open_at(gw - WW, k) : 0xffffffffu;
+    adj |= (y + 1 < H) ? open_at(gw + WW, k) : 0xffffffffu;
+    adj |= 1u << ((W - 1) & 31) & ((k == WW - 1) ? 0xffffffffu : 0u);  // right image border
+    const uint32_t M = C & adj;
+    if (!M) continue;
+    uint32_t S = C & ~(C << 1);
+    for (int j = 0; S; ++j) {
+      int s;
+      const uint32_t R = pcs_pop_run(C, S, s);
+      if (!(R & M)) continue;
+      const int r = pcs_hole_root(par, NW, pcs_node<4>(gw, j));
+      par[pcs_slot<4>(r, NW)] = PCS_MARK;
+    }
+  }
+}
+
+// thread per word: refined = kept | candidate runs whose root is unmarked (closed: a hole); bits + optional uint8 copy
+__global__ void __launch_bounds__(PCS_CCL_THREADS)
+    k_hole_select(const uint32_t* __restrict__ kept, const uint32_t* __restrict__ cand, const int* __restrict__ hpar,
+                  uint32_t* __restrict__ out, uint8_t* __restrict__ mask, int H, int W, int WW) {
+  const int NW = H * WW;
+  const int gw = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gw >= NW) return;
+  const long long b = blockIdx.y;
+  const long long t = b * NW + gw;
+  uint32_t o = __ldg(kept + t);
+  const uint32_t C = __ldg(cand + t);
+  if (C) {
+    const int* par = hpar + b * ((long long)NW << 4);
+    uint32_t S = C & ~(C << 1);
+    for (int j = 0; S; ++j) {
+      int s;
+      const uint32_t R = pcs_pop_run(C, S, s);
+      const int r = pcs_hole_root(par, NW, pcs_node<4>(gw, j));
+      if (pcs_ld_cg(par + pcs_slot<4>(r, NW)) >= 0) o |= R;
+    }
+  }
+  out[t] = o;
+  if (mask) {
+    const int y = gw / WW, k = gw - y * WW;
+    pcs_store_mask_bytes(mask + (b * H + y) * (long long)W, k, W, o);
   }
 }
 
@@ -980,6 +1132,35 @@ int pcs_ccl_scan_offsets(const PcsCclWs& ws, int32_t* counts, int B, int H, int 
   PCS_LAUNCH("k_ccl_scan", st, k_ccl_scan<<<B, 1024, 0, st>>>(ws.chunk, counts, H * CPR));
   PCS_LAUNCH("k_ccl_offsets", st, k_ccl_offsets<<<1, 1024, 0, st>>>(counts, ws.offsets, B));
   return pcs_check_launch("ccl scan");
+}
+
+// The refine stage of the pipeline (remove_small_objects + binary_fill_holes, tiff_analysis.py:769-773, :880) on the
+// labelled mask: run labels from the parent planes, hole candidates resolved over their list.  kept / cand: bit
+// planes of scratch; hpar: parent planes of scratch (B * 16 * NW ints); clist / ccount: B * NW / B ints.
+int pcs_seg_refine_stage(const uint32_t* bits, const int* labpar, const int64_t* table, int64_t cap, const int32_t* offsets,
+                         int64_t min_size, uint32_t* out, uint8_t* out_mask, uint32_t* kept, uint32_t* cand, int* hpar, int* clist,
+                         int* ccount, int B, int H, int W, cudaStream_t st) {
+  const int WW = pcs_words(W);
+  const long long NW = (long long)H * WW, rows = (long long)B * H;
+  const size_t warp_bytes = refine_words_per_warp(WW) * 4;
+  int warps = (int)(REFINE_SMEM_LIMIT / warp_bytes);
+  PCS_REQUIRE(warps >= 1, "row too wide for the refine kernel");
+  if (warps > REFINE_MAX_WARPS) warps = REFINE_MAX_WARPS;
+  static bool attr_set[64] = {};
+  if (pcs_first_use(attr_set)) cudaFuncSetAttribute(k_refine_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, REFINE_SMEM_LIMIT);
+  cudaMemsetAsync(ccount, 0, (size_t)B * 4, st);
+  PCS_LAUNCH("k_refine_rows", st, (k_refine_rows<true><<<pcs_blocks(rows, warps), warps * 32, warps * warp_bytes, st>>>(
+      bits, nullptr, (const long long*)table, cap, offsets, min_size > 1 ? min_size : 1, kept, cand, rows, H, W, WW,
+      PcsRefineSparse{labpar, hpar, clist, ccount})));
+  // candidates are rare: a few CTAs per slice cover the usual list, the grid-stride loop the unusual one
+  long long gx = (NW / 64 + HOLE_LIST_THREADS - 1) / HOLE_LIST_THREADS;
+  if (gx < 1) gx = 1;
+  if (gx > 256) gx = 256;
+  dim3 gl((unsigned)gx, B);
+  PCS_LAUNCH("k_hole_union_list", st, (k_hole_union_list<<<gl, HOLE_LIST_THREADS, 0, st>>>(cand, hpar, clist, ccount, H, WW)));
+  PCS_LAUNCH("k_hole_mark_list", st, (k_hole_mark_list<<<gl, HOLE_LIST_THREADS, 0, st>>>(kept, cand, hpar, clist, ccount, H, W, WW)));
+  PCS_LAUNCH("k_hole_select", st, (k_hole_select<<<dim3(pcs_blocks(NW, PCS_CCL_THREADS), B), PCS_CCL_THREADS, 0, st>>>(kept, cand, hpar, out, out_mask, H, W, WW)));
+  return pcs_check_launch("segment: refine stage");
 }
 
 static int check_dims(int B, int H, int W) {
@@ -1090,9 +1271,9 @@ int pcs_refine_labeled_bits(const uint32_t* bits, const int32_t* labels, const i
   PCS_REQUIRE(warps >= 1, "row too wide for the refine kernel");
   if (warps > REFINE_MAX_WARPS) warps = REFINE_MAX_WARPS;
   static bool attr_set[64] = {};
-  if (pcs_first_use(attr_set)) cudaFuncSetAttribute(k_refine_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, REFINE_SMEM_LIMIT);
-  PCS_LAUNCH("k_refine_rows", st, (k_refine_rows<<<pcs_blocks(rows, warps), warps * 32, warps * warp_bytes, st>>>(
-      bits, labels, (const long long*)table, cap, offsets, min_size, kept, cand, rows, H, W, WW)));
+  if (pcs_first_use(attr_set)) cudaFuncSetAttribute(k_refine_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, REFINE_SMEM_LIMIT);
+  PCS_LAUNCH("k_refine_rows", st, (k_refine_rows<false><<<pcs_blocks(rows, warps), warps * 32, warps * warp_bytes, st>>>(
+      bits, labels, (const long long*)table, cap, offsets, min_size, kept, cand, rows, H, W, WW, PcsRefineSparse{})));
   dim3 gw(pcs_blocks((long long)H * WW, PCS_CCL_THREADS), B);
   dim3 gq(pcs_blocks((long long)H * ((WW + 3) / 4), PCS_CCL_THREADS), B);  // groups of 4 words
   PCS_LAUNCH("k_hole_seeds", st, (k_hole_seeds<<<dim3(pcs_blocks((long long)H * ((WW + 3) / 4), 256), B), 256, 0, st>>>(kept, cand, seed, B, H, W, WW)));

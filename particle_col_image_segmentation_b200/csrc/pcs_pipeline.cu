@@ -94,7 +94,15 @@ int pcs_segment_chunk(const uint16_t* img, int B, int H, int W, int denoise_size
   if (ftable) STEP(pcs_table_finalize(table, cap, offsets, B, W, (double)z0, ftable, stream));
   // small objects out and holes filled in one call: areas come from the table just built, and only
   // row gaps between two runs of one label can hold hole pixels
-  STEP(pcs_refine_labeled_bits(bits, labels, table, cap, offsets, min_size > 1 ? min_size : 1, w.refined, refined, B, H, W, w.ccl, w.ccl_bytes, stream));
+  if (fused) {
+    // labels come from the parent planes, hole candidates are resolved over their list; the run-sum planes and the
+    // word list of the labelling stage are free by now and serve as the hole forest and the candidate list
+    PcsCclWs cw;
+    STEP(pcs_ccl_ws_carve(w.ccl, w.ccl_bytes, B, H, W, 0, &cw));
+    STEP(pcs_seg_refine_stage(bits, cw.parent, table, cap, offsets, min_size, w.refined, refined, w.keep, w.raw, w.rsum, w.wlist, w.wcount, B, H, W, (cudaStream_t)stream));
+  } else {
+    STEP(pcs_refine_labeled_bits(bits, labels, table, cap, offsets, min_size > 1 ? min_size : 1, w.refined, refined, B, H, W, w.ccl, w.ccl_bytes, stream));
+  }
   STEP(pcs_edt_bits(w.refined, 0, B, H, W, edt, nullptr, nullptr, 0, w.edt, w.edt_bytes, stream));
 #undef STEP
   return PCS_OK;
