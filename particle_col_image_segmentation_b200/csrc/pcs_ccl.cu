@@ -818,11 +818,6 @@ __global__ void __launch_bounds__(REFINE_MAX_WARPS * 32)
   int* diff = (int*)(cb + WW);                                                // WW + 1: whole-word coverage, differenced
   int* rl = diff + WW + 1;                                                    // labels of the kept runs, row order
   uint32_t* rse = (uint32_t*)(rl + REFINE_RMAX);                              // start | end << 16 of the kept runs
-  for (int k = lane; k < WW; k += 32) {
-    cb[k] = 0u;
-    diff[k] = 0;
-  }
-  if (lane == 0) diff[WW] = 0;
   const long long b = row / H;
   const int y = (int)(row - b * H);
   const int NW = H * WW;
@@ -903,7 +898,32 @@ __global__ void __launch_bounds__(REFINE_MAX_WARPS * 32)
     }
     return;
   }
+  // Most rows of a blob-like mask have no gap between two runs of one label at all: the pairing is searched once
+  // without painting, and such rows leave with an all-zero candidate row -- no scratch to clear, no prefix scan.
   int fb = -1;  // end of the row prefix painted when a search window ran out
+  bool pair = false;
+  for (int i = lane; i < n; i += 32) {
+    const int L = rl[i];
+    const int lo = max(i - REFINE_K, 0);
+    int j = i - 1;
+    while (j >= lo && rl[j] != L) --j;
+    const int e = (int)(rse[i] & 0xffffu) - 1;
+    if (j >= lo) {
+      pair |= (int)(rse[j] >> 16) + 1 <= e;
+    } else if (lo > 0) {
+      fb = max(fb, e);
+    }
+  }
+  if (!__any_sync(0xffffffffu, pair || fb >= 0)) {
+    for (int k = lane; k < WW; k += 32) cand_out[row * (long long)WW + k] = 0u;
+    return;
+  }
+  for (int k = lane; k < WW; k += 32) {
+    cb[k] = 0u;
+    diff[k] = 0;
+  }
+  if (lane == 0) diff[WW] = 0;
+  __syncwarp();
   for (int i = lane; i < n; i += 32) {
     const int L = rl[i];
     const int lo = max(i - REFINE_K, 0);
@@ -913,8 +933,6 @@ __global__ void __launch_bounds__(REFINE_MAX_WARPS * 32)
     if (j >= lo) {
       const int a = (int)(rse[j] >> 16) + 1;
       if (a <= e) refine_paint(cb, diff, a, e);
-    } else if (lo > 0) {
-      fb = max(fb, e);
     }
   }
   fb = __reduce_max_sync(0xffffffffu, fb);
@@ -1125,6 +1143,14 @@ static int ccl_label(const P& prov, int B, int conn, void* labels, int label_byt
     PCS_LAUNCH("k_ccl_relabel", st, k_ccl_relabel<P, long long><<<gc, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, (long long*)labels, B, CPR));
   if (offsets_out) cudaMemcpyAsync(offsets_out, ws.offsets, (size_t)(B + 1) * 4, cudaMemcpyDeviceToDevice, st);
   return pcs_check_launch("ccl label");
+}
+
+int pcs_ccl_relabel_bin(const uint32_t* bits, const PcsCclWs& ws, int32_t* labels, int B, int H, int W, cudaStream_t st) {
+  PcsBinProv prov{bits, H, W, pcs_words(W), 0};
+  const int CPR = (prov.WW + 31) / 32;
+  dim3 gc(pcs_blocks((long long)H * CPR * 32, PCS_CCL_THREADS), B);
+  PCS_LAUNCH("k_ccl_relabel", st, (k_ccl_relabel<PcsBinProv, int32_t><<<gc, PCS_CCL_THREADS, 0, st>>>(prov, ws.parent, labels, B, CPR)));
+  return pcs_check_launch("ccl relabel");
 }
 
 int pcs_ccl_scan_offsets(const PcsCclWs& ws, int32_t* counts, int B, int H, int W, cudaStream_t st) {

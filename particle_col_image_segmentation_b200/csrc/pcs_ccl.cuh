@@ -175,6 +175,8 @@ int pcs_ccl_ws_carve(void* ws, size_t ws_bytes, int B, int H, int W, int with_au
 // ---- pieces of the labeller the fused segment pipeline drives itself (pcs_segment.cu, pcs_pipeline.cu)
 // exclusive scan of ws.chunk per slice (in place), per-slice totals -> counts, exclusive scan of those -> ws.offsets
 int pcs_ccl_scan_offsets(const PcsCclWs& ws, int32_t* counts, int B, int H, int W, cudaStream_t st);
+// labels of a binary mask whose parent planes hold the (negated) label or the root of every run -> int32 image
+int pcs_ccl_relabel_bin(const uint32_t* bits, const PcsCclWs& ws, int32_t* labels, int B, int H, int W, cudaStream_t st);
 int pcs_seg_label_stage(const uint16_t* img, const int32_t* thr, int median, uint32_t* bits, uint8_t* mask, int32_t* labels,
                         int32_t* counts, int64_t* table, int64_t cap, const PcsCclWs& ws, int* rsum, int* wlist, int* wcount, int B, int H,
                         int W, cudaStream_t st);

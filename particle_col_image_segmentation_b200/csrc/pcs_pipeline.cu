@@ -42,7 +42,7 @@ size_t seg_carve(void* ws, int B, int H, int W, SegWs* out) {
   w.edt = take(w.edt_bytes);
   w.rsum = (int*)take((size_t)B * H * pcs_words(W) * 16 * 4);
   w.wlist = (int*)take((size_t)B * H * pcs_words(W) * 4);
-  w.wcount = (int*)take((size_t)B * 4);
+  w.wcount = (int*)take((size_t)(B + 1) * 4);
   if (out) *out = w;
   return n;
 }

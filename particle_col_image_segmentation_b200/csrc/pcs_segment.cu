@@ -389,6 +389,68 @@ __global__ void __launch_bounds__(SEG_LIST_THREADS)
   }
 }
 
+// block per slice: exclusive scan of the slice's chunk counts (raster order) and the slice total; the block that
+// finishes last also scans the totals into the table row offsets (one launch instead of two: both are latency-only)
+__global__ void __launch_bounds__(1024)
+    k_seg_scan_offsets(int* __restrict__ chunk, int32_t* __restrict__ counts, int n, int* __restrict__ offsets, int* __restrict__ done, int B) {
+  __shared__ int wsum[32];
+  __shared__ int carry_s;
+  __shared__ int is_last;
+  int* c = chunk + (long long)blockIdx.x * n;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int i = base + tid;
+    const int v = i < n ? c[i] : 0;
+    const int carry = carry_s;  // stable here: last written before the previous iteration's barriers
+    int tot;
+    const int ex = pcs_warp_excl_scan(v, lane, &tot);
+    if (lane == 0) wsum[wid] = tot;
+    __syncthreads();
+    if (wid == 0) {
+      const int w = lane < (int)(blockDim.x >> 5) ? wsum[lane] : 0;
+      int wt;
+      const int wex = pcs_warp_excl_scan(w, lane, &wt);
+      wsum[lane] = wex;
+      if (lane == 0) carry_s = carry + wt;
+    }
+    __syncthreads();
+    if (i < n) c[i] = carry + wsum[wid] + ex;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    counts[blockIdx.x] = carry_s;
+    __threadfence();
+    is_last = atomicAdd(done, 1) == (int)gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < B; base += blockDim.x) {
+    const int i = base + tid;
+    const int v = i < B ? __ldcg(counts + i) : 0;
+    const int carry = carry_s;
+    int tot;
+    const int ex = pcs_warp_excl_scan(v, lane, &tot);
+    if (lane == 0) wsum[wid] = tot;
+    __syncthreads();
+    if (wid == 0) {
+      const int w = wsum[lane];
+      int wt;
+      const int wex = pcs_warp_excl_scan(w, lane, &wt);
+      wsum[lane] = wex;
+      if (lane == 0) carry_s = carry + wt;
+    }
+    __syncthreads();
+    if (i < B) offsets[i] = carry + wsum[wid] + ex;
+    __syncthreads();
+  }
+  if (tid == 0) offsets[B] = carry_s;
+}
+
 // roots get their raster-order rank (stored negated in the parent plane) and their table row is initialised.  The
 // rank of a root = roots of the slice before its 32-word chunk (scanned chunk counts) + roots in the chunk's earlier
 // words + its ordinal among the roots of its own word.  A root is the first raster pixel of its component, so the
@@ -627,6 +689,84 @@ __global__ void __launch_bounds__(SEG_RL_WARPS * 32)
   seg_flush(acc, table, cap, tbase);
 }
 
+// every run gets its label (root rank) written back, negated, in place of its parent -- the expansion to pixels and
+// the refine stage then read labels with ONE load per run -- and adds its area, coordinate sums, horizontal extent,
+// bottom row and intensity sum to its component's table row.  All of a thread's loads are independent of every other
+// thread's, so the node -> root -> rank chain is hidden by thread-level parallelism alone.
+// Warp aggregation before the global atomics: consecutive list entries are neighbouring words of a tile, so several
+// lanes of a warp usually carry the same label.  __match_any_sync groups them, REDUX (__reduce_*_sync over the group's
+// mask; per-warp partial sums fit 32 bits) folds the seven quantities and the group's first lane issues the atomics:
+// about a third of the atomics of the one-per-run version.
+__device__ __forceinline__ void seg_table_add(long long* __restrict__ table, long long cap, long long row, int area, int sy, int sx,
+                                              int si, int minx, int maxx, int maxy) {
+  typedef unsigned long long ull;
+  atomicAdd((ull*)(table + T_AREA * cap + row), (ull)area);
+  atomicAdd((ull*)(table + T_SUMY * cap + row), (ull)sy);
+  atomicAdd((ull*)(table + T_SUMX * cap + row), (ull)sx);
+  atomicAdd((ull*)(table + T_SUMI * cap + row), (ull)si);
+  atomicMin(table + T_MINX * cap + row, (long long)minx);
+  atomicMax(table + T_MAXY * cap + row, (long long)maxy);
+  atomicMax(table + T_MAXX * cap + row, (long long)maxx);
+}
+
+__global__ void __launch_bounds__(SEG_LIST_THREADS)
+    k_seg_label_list(const uint32_t* __restrict__ bits, int* __restrict__ parent, const int* __restrict__ rsum,
+                     const int* __restrict__ wlist, const int* __restrict__ wcount, const int* __restrict__ offsets,
+                     long long* __restrict__ table, long long cap, int H, int W, int WW) {
+  const long long b = blockIdx.y;
+  const int NW = H * WW;
+  const int n = min(wcount[b], NW);
+  const uint32_t* bb = bits + b * (long long)NW;
+  int* par = parent + b * ((long long)NW << SEG_LSPW);
+  const int* rs = rsum + b * ((long long)NW << SEG_LSPW);
+  const int* wl = wlist + b * (long long)NW;
+  const long long trow = offsets[b];
+  const int lane = threadIdx.x & 31;
+  // warp-uniform trip count: lanes past the end of the list take part in the votes with nothing to add
+  for (int it0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); it0 < n; it0 += gridDim.x * blockDim.x) {
+    const int it = it0 + lane;
+    const bool valid = it < n;
+    int l0 = 0, area = 0, sy = 0, sx = 0, si = 0, minx = 0x7fffffff, maxx = -1, y = 0;
+    if (valid) {
+      const int gw = wl[it];
+      const uint32_t F = __ldg(bb + gw);
+      y = gw / WW;
+      const int x0 = (gw - y * WW) << 5;
+      uint32_t S = F & ~(F << 1);
+      for (int j = 0; S; ++j) {
+        int s;
+        const uint32_t R = pcs_pop_run(F, S, s);
+        const int p0 = par[j * NW + gw];
+        const int rsi = rs[j * NW + gw];
+        int l;
+        if (p0 < 0) {
+          l = -p0;  // a root: already ranked
+        } else {
+          l = -par[pcs_slot<SEG_LSPW>(p0, NW)];
+          par[j * NW + gw] = -l;
+        }
+        const int len = __popc(R), xs = x0 + s;
+        const int rsy = len * y, rsx = len * xs + len * (len - 1) / 2;
+        if (j == 0) {  // the word's first run goes through the warp aggregation
+          l0 = l;
+          area = len, sy = rsy, sx = rsx, si = rsi, minx = xs, maxx = xs + len - 1;
+        } else if (trow + l - 1 < cap) {
+          seg_table_add(table, cap, trow + l - 1, len, rsy, rsx, rsi, xs, xs + len - 1, y);
+        }
+      }
+    }
+    const unsigned grp = __match_any_sync(0xffffffffu, l0);
+    area = __reduce_add_sync(grp, area);
+    sy = __reduce_add_sync(grp, sy);
+    sx = __reduce_add_sync(grp, sx);
+    si = __reduce_add_sync(grp, si);
+    minx = __reduce_min_sync(grp, minx);
+    maxx = __reduce_max_sync(grp, maxx);
+    y = __reduce_max_sync(grp, y);
+    if (l0 > 0 && lane == __ffs(grp) - 1 && trow + l0 - 1 < cap) seg_table_add(table, cap, trow + l0 - 1, area, sy, sx, si, minx, maxx, y);
+  }
+}
+
 // ============================================================== host side
 // The labelling stage of the pipeline: img, thr -> bits, uint8 mask, int32 labels, counts, offsets, region table.
 int pcs_seg_label_stage(const uint16_t* img, const int32_t* thr, int median, uint32_t* bits, uint8_t* mask, int32_t* labels,
@@ -635,7 +775,7 @@ int pcs_seg_label_stage(const uint16_t* img, const int32_t* thr, int median, uin
   const int WW = pcs_words(W), CPR = (WW + 31) / 32;
   const long long NW = (long long)H * WW;
   PCS_REQUIRE(B <= 65535 && (H + SEG_TR - 1) / SEG_TR <= 65535, "grid too large for the tile kernel");
-  cudaMemsetAsync(wcount, 0, (size_t)B * 4, st);
+  cudaMemsetAsync(wcount, 0, (size_t)(B + 1) * 4, st);
   cudaMemsetAsync(ws.rootbits, 0, (size_t)B * NW * 4, st);
   cudaMemsetAsync(ws.chunk, 0, (size_t)B * H * CPR * 4, st);
   dim3 gt((WW + SEG_TW - 1) / SEG_TW, (H + SEG_TR - 1) / SEG_TR, B);
@@ -650,11 +790,17 @@ int pcs_seg_label_stage(const uint16_t* img, const int32_t* thr, int median, uin
   dim3 gl((unsigned)gx, B);
   PCS_LAUNCH("k_seg_merge_list", st, (k_seg_merge_list<<<gl, SEG_LIST_THREADS, 0, st>>>(bits, ws.parent, wlist, wcount, H, W, WW)));
   PCS_LAUNCH("k_seg_flatten_list", st, (k_seg_flatten_list<<<gl, SEG_LIST_THREADS, 0, st>>>(bits, ws.parent, wlist, wcount, ws.rootbits, ws.chunk, H, W, WW, CPR)));
-  int rc = pcs_ccl_scan_offsets(ws, counts, B, H, W, st);
-  if (rc) return rc;
+  int rc = PCS_OK;
+  PCS_LAUNCH("k_seg_scan_offsets", st, (k_seg_scan_offsets<<<B, 1024, 0, st>>>(ws.chunk, counts, H * CPR, ws.offsets, wcount + B, B)));  // wcount[B]: the "blocks done" counter, zeroed with the list counts
   PCS_LAUNCH("k_seg_rank_list", st, (k_seg_rank_list<<<gl, SEG_LIST_THREADS, 0, st>>>(bits, ws.parent, wlist, wcount, ws.rootbits, ws.chunk, ws.offsets, (long long*)table, cap, H, W, WW, CPR)));
+#ifdef SEG_FUSED_RELABEL_TABLE
   const int strips = (H + SEG_RROWS - 1) / SEG_RROWS;
   dim3 gr(pcs_blocks((long long)strips * CPR * 32, SEG_RL_WARPS * 32), B);
   PCS_LAUNCH("k_seg_relabel_table", st, (k_seg_relabel_table<int32_t><<<gr, SEG_RL_WARPS * 32, 0, st>>>(bits, ws.parent, rsum, ws.offsets, (long long*)table, cap, labels, H, W, WW, CPR, strips)));
+#else
+  PCS_LAUNCH("k_seg_label_list", st, (k_seg_label_list<<<gl, SEG_LIST_THREADS, 0, st>>>(bits, ws.parent, rsum, wlist, wcount, ws.offsets, (long long*)table, cap, H, W, WW)));
+  rc = pcs_ccl_relabel_bin(bits, ws, labels, B, H, W, st);
+  if (rc) return rc;
+#endif
   return pcs_check_launch("segment: labelling stage");
 }
