@@ -827,47 +827,82 @@ __global__ void __launch_bounds__(REFINE_MAX_WARPS * 32)
   const uint32_t* frow = fg + row * (long long)WW;
   int n = 0;
   bool overflow = false;
-  for (int k0 = 0; k0 < WW; k0 += 32) {
-    const int k = k0 + lane;
-    const uint32_t f = k < WW ? __ldg(frow + k) : 0u;
-    uint32_t kept = f;
-    int cnt = __popc(f & ~(f << 1));
-    if (min_size > 1) {
-      kept = 0u;
-      cnt = 0;
-      uint32_t S = f & ~(f << 1);
-      for (int j = 0; S; ++j) {
-        const int s = __ffs(S) - 1;
-        S &= S - 1;
-        const uint32_t upper = ~(f >> s);
-        const int len = upper ? (__ffs(upper) - 1) : 32;
-        const long long r = tbase + (PLANES ? -lpl[j * NW + k] : __ldg(lrow + (k << 5) + s)) - 1;
-        if (r < 0 || r >= cap || __ldg(table + r) < min_size) continue;  // column 0 of the table: area
-        kept |= (len >= 32 ? 0xffffffffu : ((1u << len) - 1u)) << s;
-        ++cnt;
+  // Four 32-word groups at a time: the words, then the label of every word's first run, then its area are requested
+  // for all four before any is used, so a row waits for three memory round trips per 128 words (the word -> label ->
+  // area chain, once per group, was a third of this kernel's stall samples).
+  for (int kb = 0; kb < WW; kb += 128) {
+    uint32_t f4[4];
+    int L4[4];
+    long long A4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = kb + 32 * u + lane;
+      f4[u] = k < WW ? __ldg(frow + k) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = kb + 32 * u + lane;
+      L4[u] = 0;
+      if (f4[u]) L4[u] = PLANES ? -lpl[k] : __ldg(lrow + (k << 5) + __ffs(f4[u]) - 1);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      A4[u] = 0;
+      if (min_size > 1 && f4[u]) {
+        const long long r = tbase + L4[u] - 1;
+        A4[u] = (r < 0 || r >= cap) ? 0 : __ldg(table + r);  // column 0 of the table: area
       }
     }
-    int tot;
-    int at = n + pcs_warp_excl_scan(cnt, lane, &tot);
-    n += tot;
-    overflow |= n > REFINE_RMAX;
-    if (!overflow) {
-      uint32_t S = kept & ~(kept << 1);
-      const uint32_t Sf = f & ~(f << 1);  // the ordinal of a kept run counts the dropped runs of the word too
-      while (S) {  // labels come back from L1 this time
-        const int s = __ffs(S) - 1;
-        S &= S - 1;
-        const uint32_t upper = ~(kept >> s);
-        const int len = upper ? (__ffs(upper) - 1) : 32;
-        const uint32_t xs = (uint32_t)((k << 5) + s);
-        rl[at] = PLANES ? -lpl[pcs_run_ord(Sf, s) * NW + k] : __ldg(lrow + xs);
-        rse[at] = xs | ((xs + len - 1) << 16);
-        ++at;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k0 = kb + 32 * u;
+      if (k0 >= WW) break;  // warp-uniform
+      const int k = k0 + lane;
+      const uint32_t f = f4[u];
+      uint32_t kept = f;
+      int cnt = __popc(f & ~(f << 1));
+      if (min_size > 1) {
+        kept = 0u;
+        cnt = 0;
+        uint32_t S = f & ~(f << 1);
+        for (int j = 0; S; ++j) {
+          const int s = __ffs(S) - 1;
+          S &= S - 1;
+          const uint32_t upper = ~(f >> s);
+          const int len = upper ? (__ffs(upper) - 1) : 32;
+          long long area = A4[u];
+          if (j > 0) {
+            const long long r = tbase + (PLANES ? -lpl[j * NW + k] : __ldg(lrow + (k << 5) + s)) - 1;
+            area = (r < 0 || r >= cap) ? 0 : __ldg(table + r);
+          }
+          if (area < min_size) continue;
+          kept |= (len >= 32 ? 0xffffffffu : ((1u << len) - 1u)) << s;
+          ++cnt;
+        }
       }
-    }
-    if (k < WW) {
-      kw[k] = kept;
-      kept_out[row * (long long)WW + k] = kept;
+      int tot;
+      int at = n + pcs_warp_excl_scan(cnt, lane, &tot);
+      n += tot;
+      overflow |= n > REFINE_RMAX;
+      if (!overflow) {
+        uint32_t S = kept & ~(kept << 1);
+        const uint32_t Sf = f & ~(f << 1);  // the ordinal of a kept run counts the dropped runs of the word too
+        while (S) {
+          const int s = __ffs(S) - 1;
+          S &= S - 1;
+          const uint32_t upper = ~(kept >> s);
+          const int len = upper ? (__ffs(upper) - 1) : 32;
+          const uint32_t xs = (uint32_t)((k << 5) + s);
+          const int ord = pcs_run_ord(Sf, s);
+          rl[at] = ord == 0 ? L4[u] : (PLANES ? -lpl[ord * NW + k] : __ldg(lrow + xs));
+          rse[at] = xs | ((xs + len - 1) << 16);
+          ++at;
+        }
+      }
+      if (k < WW) {
+        kw[k] = kept;
+        kept_out[row * (long long)WW + k] = kept;
+      }
     }
   }
   __syncwarp();
