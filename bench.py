@@ -31,6 +31,12 @@ SUM_OF_STAGES_BYTES_PER_VOXEL = 27.0
 # read once + outputs that must be written once, bit images counted as 1/8 B
 KERNEL_BYTES_PER_VOXEL = {
     "k_hist_u16": 2.0,
+    "k_seg_threshold_tile": 2.0 + 1.0 + 0.125,  # uint16 in, uint8 mask + bit rows out (parents / run sums / word list are sparse)
+    "k_seg_merge_list": 0.125,
+    "k_seg_flatten_list": 0.125,
+    "k_seg_rank_list": 0.125,
+    "k_seg_label_list": 0.125,
+    "k_seg_relabel_table": 4.0 + 0.125,
     "k_compare": 2.0 + 0.125,
     "k_majority5_bits": 0.25 + 1.0,
     "k_unpack": 1.0 + 0.125,
@@ -41,6 +47,8 @@ KERNEL_BYTES_PER_VOXEL = {
     "k_ccl_relabel": 4.0 + 0.125,
     "k_ccl_mark": 0.125,
     "k_ccl_select": 0.25 + 1.0,
+    "k_refine_rows": 0.375,
+    "k_hole_select": 0.375 + 1.0,
     "k_bbox_raster": 0.125,
     "k_hole_candidates": 0.5,
     "k_region_table": 4.0 + 2.0,
@@ -116,7 +124,7 @@ def _cpu_one(i):
     return time.perf_counter() - t, int(r["labels"].max())
 
 
-def cpu_reference(size, n_sample, steps=1, warmup=0):
+def cpu_reference(size, n_sample, steps=1, warmup=0, procs_cap=None):
     """Times the oracle (the reference's scipy / scikit-image composition) on host cores.
     Returns (Mvoxel/s, cores used, description, ms per step)."""
     import multiprocessing as mp
@@ -125,7 +133,7 @@ def cpu_reference(size, n_sample, steps=1, warmup=0):
 
     global _SAMPLE
     cores = os.cpu_count() or 1
-    procs = max(1, min(cores, n_sample))
+    procs = max(1, min(cores, n_sample, procs_cap or cores))
     _SAMPLE = synth.zstack_u16(n_sample, size, size, seed=1002)
     ctx = mp.get_context("fork")  # workers inherit the sample; CUDA is not initialised yet
     with ctx.Pool(procs) as pool:
@@ -146,7 +154,7 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     n_sample = args.cpu_sample or max(1, min(cores, 32))
-    mvox, procs, desc, ms = cpu_reference(args.size, n_sample, steps=args.steps, warmup=min(args.warmup, 1))
+    mvox, procs, desc, ms = cpu_reference(args.size, n_sample, steps=args.steps, warmup=args.warmup)
     line = {
         "impl": "reference",
         "metric": METRIC,
@@ -154,7 +162,7 @@ def run_reference(args):
         "unit": "Mvoxel/s",
         "n_gpus": args.gpus,
         "steps": args.steps,
-        "warmup": min(args.warmup, 1),
+        "warmup": args.warmup,
         "ms_per_step": ms,
         "higher_is_better": True,
         "scaling": "weak",
@@ -261,7 +269,9 @@ def run_b200(args):
         cores = os.cpu_count() or 1
         n_sample = args.cpu_sample or max(1, min(cores, 32))
         mvox, procs, desc, _ = cpu_reference(S, n_sample)  # before CUDA is initialised (fork)
-        cpu = {"value": mvox, "unit": "Mvoxel/s", "cores": procs, "kind": "port", "sample": desc}
+        mv1, _, d1, _ = cpu_reference(S, 2, procs_cap=1)      # how the reference itself runs: one thread
+        cpu = {"value": mvox, "unit": "Mvoxel/s", "cores": procs, "kind": "port", "sample": desc,
+               "single_thread": {"value": mv1, "unit": "Mvoxel/s", "cores": 1, "sample": d1}}
 
     import torch
     import torch.distributed as dist
@@ -284,15 +294,14 @@ def run_b200(args):
     res = plan_eager.out
     plan = split_zstack.SegmentPlan(stack, chunk=args.chunk, z0=rank * Z, out=None, graph=True, streams=args.streams) if not args.no_graph else plan_eager
 
-    gatherers = []
+    gatherer = pdist.TableGather()  # one gather-to-root per step: header with the row counts + the rows of every chunk
+    last_exchange = [None]
 
     def step(p=None):
         r = (p or plan)()
-        if world > 1 and not args.no_gather:  # the one exchange step: row counts and rows, no host sync in the steady state (dist.TableGather)
-            pads = r.table_padded()
-            while len(gatherers) < len(pads):
-                gatherers.append(pdist.TableGather())
-            table = [g(ft, off) for g, (off, ft) in zip(gatherers, pads)]  # one exchange per chunk of slices
+        if world > 1 and not args.no_gather:  # the one exchange of a step; no host sync in the steady state (dist.TableGather)
+            table = gatherer(r.table_padded())
+            last_exchange[0] = table
         else:
             table = r.table_padded()  # finished float64 table in HBM (row count in offsets[-1]); no host sync
         return r, table
@@ -328,6 +337,8 @@ def run_b200(args):
         e0.record()
         for _ in range(steps):
             step(p)
+        if last_exchange[0] is not None and last_exchange[0].ready is not None:
+            torch.cuda.current_stream().wait_event(last_exchange[0].ready)  # the interval covers the last step's completed gather
         e1.record()
         barrier()
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -346,14 +357,17 @@ def run_b200(args):
         l0 = lib.pcs_kernel_launches()
         step(plan_eager)
         launches = (lib.pcs_kernel_launches() - l0) * args.steps
-    if world > 1 and not args.no_gather:  # outside the timed region: the speculative gather must hold exactly the rows of all ranks
+    gather_check = None
+    if world > 1 and not args.no_gather:
+        # outside the timed region: the table the root gathered must equal, byte for byte, the concatenation of the
+        # ranks' own compact tables (exchanged here the plain way: counts, then padded rows)
         r_chk, g_chk = step()
-        rows = sum(int(g.compact().shape[0]) for g in g_chk)
-        n_all = torch.tensor([int(r_chk.table_device().shape[0])], dtype=torch.int64, device=dev)
-        if world > 1:
-            dist.all_reduce(n_all)
-        if rows != int(n_all.item()):
-            raise SystemExit("bench: gathered table does not hold the rows of all ranks")
+        got = g_chk.compact()
+        want = pdist.gather_tables(r_chk.table_device())
+        if rank == 0:
+            gather_check = bool(got.shape == want.shape and torch.equal(got.view(torch.int64), want.view(torch.int64)))
+            if not gather_check:
+                raise SystemExit("bench: gathered table differs from the concatenation of the per-rank tables")
     voxels = float(Z) * S * S * world
     value = voxels / (ms_step * 1e-3) / 1e6
 
@@ -421,7 +435,8 @@ def run_b200(args):
                 "write_only_gbs_live": write_only_probe(dev, lib),
                 "bytes_per_voxel": bpv, "avg_launch_ms": avg_ms, "launches": kcnt, "peak_source": peak_src, "kernel_time_share": shares,
                 "kernel_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
-                "timed": "per-kernel CUDA events on the launching stream over a second pass of the same K steps (eager launches)", "ms_per_step_with_events": ms_step_profiled}
+                "timed": "per-kernel CUDA events on the launching stream over a second pass of the same K steps (eager launches, one stream): the pairs inflate the step, shares are exact, absolute per-kernel ms are high by about event_inflation",
+                "ms_per_step_with_events": ms_step_profiled, "event_inflation": (sum(v[0] for v in prof.values()) / args.steps) / ms_step}
     per_gpu = value / world * 1e6
     line = {
         "metric": METRIC,
@@ -437,7 +452,8 @@ def run_b200(args):
         "dtype": "u16",
         "data": "synthetic",
         "config": {"workload": f"split_zstack + segment a synthetic {S}x{S}x{Z} uint16 z-stack per GPU (BASELINE.json configs[1])", "size": S, "slices_per_gpu": Z, "chunk": args.chunk, "streams": args.streams, "launch": "eager" if args.no_graph else "cuda graph replay (one graph per step)",
-                   "l2": "input stack (%.0f MiB) and outputs are larger than L2; no flush needed" % (Z * S * S * 2 / 2**20), "parity_spot_check": parity},
+                   "l2": "input stack (%.0f MiB) and outputs are larger than L2; no flush needed" % (Z * S * S * 2 / 2**20), "parity_spot_check": parity,
+                   "table_gather": None if world == 1 else {"collectives_per_step": 1, "kind": "gather to rank 0 (NCCL send/recv group), overlapped with the next step", "byte_equal_to_per_rank_tables": gather_check}},
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": int(launches),

@@ -3,13 +3,17 @@
 Every 2-D slice is an independent problem (tiff_analysis.py:727-737 only ever sees
 one image; split_zstack.py:52 iterates slices; labels restart at 1 per slice), so a
 stack shards by contiguous blocks of slices with no halo and no label
-reconciliation.  The only exchange is the per-label table: ranks all-gather their
-row counts, pad to the largest and all-gather the rows (NCCL on device tensors; the
-same code runs over gloo on CPU tensors in the tests).
+reconciliation.  The only exchange is the per-label table.  ``gather_tables`` /
+``gather_tables_padded`` are the plain forms (counts, then rows padded to the largest);
+``TableGather`` is what a running pipeline uses: one gather-to-root per step, no host
+synchronisation, overlapped with the next step (NCCL on device tensors; the same code
+runs over gloo on CPU tensors in the tests).
 """
 
 import torch
 import torch.distributed as dist
+
+from . import _lib
 
 
 def shard_range(n_slices, rank, world_size):
@@ -47,11 +51,16 @@ def gather_tables_padded(ftable, offsets, group=None):
     read back in ONE host synchronisation; every rank then contributes its first ``max(counts)`` rows."""
     n_local = offsets[-1:].to(torch.int64)
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return ftable[: int(n_local.item())]
+        n = int(n_local.item())
+        if n > ftable.shape[0]:
+            raise _lib.PcsError(f"region table overflow: {n} regions, capacity {ftable.shape[0]}; raise max_regions_per_slice")
+        return ftable[:n]
     world = dist.get_world_size(group)
     counts = torch.empty(world, dtype=torch.int64, device=ftable.device)
     dist.all_gather_into_tensor(counts, n_local, group=group)
     counts = counts.cpu().tolist()
+    if max(counts) > ftable.shape[0]:
+        raise _lib.PcsError(f"region table overflow: {max(counts)} regions, capacity {ftable.shape[0]}; raise max_regions_per_slice")
     cap = min(max(max(counts), 1), ftable.shape[0])
     flat = torch.empty((world * cap, ftable.shape[1]), dtype=ftable.dtype, device=ftable.device)
     dist.all_gather_into_tensor(flat, ftable[:cap].contiguous(), group=group)
@@ -60,87 +69,137 @@ def gather_tables_padded(ftable, offsets, group=None):
 
 
 class GatheredTable:
-    """Result of ``TableGather``: every rank's first ``cap`` rows and all row counts, still on the device.
-    ``compact()`` waits for the exchange, reads the counts (the one host synchronisation) and returns the
-    ``(sum n_r, C)`` table."""
+    """Result of ``TableGather``: on the root (or on every rank with ``all_ranks=True``) the staged rows and row
+    counts of all ranks, still on the device.  ``compact()`` waits for the exchange, reads the counts (the one host
+    synchronisation) and returns the ``(sum n, C)`` table in (rank, chunk) order, i.e. global slice order; on ranks
+    that received nothing it returns ``None``."""
 
-    def __init__(self, parts, counts, cap, redo, ready=None):
-        self.parts, self.counts, self.cap, self._redo, self.ready = parts, counts, cap, redo, ready
+    def __init__(self, owner, recv, caps, hdr_rows, table_caps, ready=None):
+        self.owner, self.recv, self.caps, self.hdr_rows, self.table_caps, self.ready = owner, recv, caps, hdr_rows, table_caps, ready
 
     def compact(self):
         if self.ready is not None:
             self.ready.synchronize()
-        counts = self.counts.cpu().tolist()
-        if max(counts) > self.cap:  # the speculative capacity was too small: exchange again with the true sizes
-            return self._redo()
-        return torch.cat([self.parts[r, :c] for r, c in enumerate(counts)], dim=0)
+        if self.recv is None:
+            return None
+        nch, C = len(self.caps), self.recv.shape[2]
+        counts = self.recv[:, : self.hdr_rows].reshape(self.recv.shape[0], -1)[:, :nch].cpu().to(torch.int64)
+        for i, (cap, tcap) in enumerate(zip(self.caps, self.table_caps)):
+            worst = int(counts[:, i].max())
+            if worst > tcap:
+                raise _lib.PcsError(f"region table overflow: {worst} regions in a chunk, capacity {tcap}; raise max_regions_per_slice")
+            if worst > cap:
+                # The staged copy holds only `cap` rows and the pipeline may have overwritten its table since: the rows
+                # are gone.  Later exchanges use the larger capacity; this one has to be repeated by the caller.
+                self.owner.caps = None
+                self.owner.min_caps = [max(m, int(counts[:, j].max())) for j, m in enumerate(self.owner.min_caps or [0] * nch)]
+                raise _lib.PcsError(f"table gather: a chunk holds {worst} regions, the speculative capacity was {cap}; "
+                                    "the capacity has been raised, run the step and the exchange again")
+        parts, row0 = [], self.hdr_rows
+        starts = []
+        for cap in self.caps:
+            starts.append(row0)
+            row0 += cap
+        for r in range(self.recv.shape[0]):
+            for i in range(nch):
+                n = int(counts[r, i])
+                if n:
+                    parts.append(self.recv[r, starts[i] : starts[i] + n])
+        if not parts:
+            return torch.zeros((0, C), dtype=self.recv.dtype, device=self.recv.device)
+        return parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)
 
 
 class TableGather:
-    """All-gather of the padded per-rank region tables without a host synchronisation in the steady state,
-    overlapped with the next step's kernels.
+    """Gather of the per-rank region tables of one step: ONE collective per step, to the root, without a host
+    synchronisation in the steady state and without making the pipeline wait for the previous exchange.
 
-    The number of rows a rank contributes is only known on the device.  Instead of reading it back before
-    every exchange (``gather_tables_padded``), the exchange ships the first ``cap`` rows of every rank, where
-    ``cap`` is 1.25 x the largest count seen so far; the counts travel alongside and are checked when the
-    table is consumed (``GatheredTable.compact``).  A count above ``cap`` redoes that exchange with the true
-    sizes and raises the capacity, so the result is always exact.  On CUDA the rows are first copied to a
-    staging buffer on the caller's stream and the two collectives run on a side stream, so the pipeline can
-    overwrite its table for the next stack while the previous one is still travelling."""
+    ``gather(pads)`` takes the padded device tables of all chunks of a step (``SegmentResult.table_padded()``:
+    ``(offsets, ftable)`` pairs, rows ``[0, offsets[-1])`` valid).  The number of valid rows is only known on the
+    device, so every rank ships a fixed-size message: a header row with its row counts followed by the first
+    ``cap_i`` rows of every chunk, where ``cap_i`` is 1.25 x the largest count seen when the sizes were learnt
+    (first call: one all-reduce of the counts and one synchronisation).  Counts are checked when the table is
+    consumed (``GatheredTable.compact``); a count above the shipped capacity raises -- the staged copy cannot be
+    completed afterwards because the pipeline may already be overwriting its tables -- and enlarges the capacity
+    for the following steps.  On CUDA the message is assembled in one of two staging buffers on the caller's stream
+    and the collective (``dist.gather``: grouped NCCL send / recv, nothing lands on the non-root ranks) runs on a
+    side stream; a staging buffer is reused only after the exchange that read it two steps earlier, so the kernels
+    of step n + 1 overlap the exchange of step n.  ``all_ranks=True`` turns the gather into an all-gather."""
 
-    def __init__(self, group=None, cap=0):
-        self.group, self.cap = group, int(cap)
-        self.comm = self.done = self.stage = self.stage_n = None
+    def __init__(self, group=None, root=0, all_ranks=False, slack=1.25):
+        self.group, self.root, self.all_ranks, self.slack = group, int(root), bool(all_ranks), float(slack)
+        self.caps = self.min_caps = None
+        self.comm = None
+        self.stage, self.recv, self.done, self.k = [None, None], [None, None], [None, None], 0
 
-    def __call__(self, ftable, offsets):
-        n_local = offsets[-1:].to(torch.int64)
-        world = dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
-        if self.cap <= 0:  # first use: learn the sizes (one synchronisation)
-            if world > 1:
-                counts = torch.empty(world, dtype=torch.int64, device=ftable.device)
-                dist.all_gather_into_tensor(counts, n_local, group=self.group)
+    def _world(self):
+        return dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
+
+    def _learn(self, pads):
+        counts = torch.stack([off[-1].to(torch.int64) for off, _ in pads])
+        if self._world() > 1:
+            dist.all_reduce(counts, op=dist.ReduceOp.MAX, group=self.group)
+        worst = counts.cpu().tolist()  # the one synchronisation
+        floor = self.min_caps or [0] * len(pads)
+        self.caps = [min(max(int(max(w, m) * self.slack) + 16, 16), int(ft.shape[0])) for w, m, (_, ft) in zip(worst, floor, pads)]
+        self.stage, self.recv, self.done = [None, None], [None, None], [None, None]
+
+    def gather(self, pads):
+        if isinstance(pads, tuple) and len(pads) == 2 and torch.is_tensor(pads[0]):
+            pads = [pads]
+        world = self._world()
+        rank = dist.get_rank(self.group) if world > 1 else 0
+        if self.caps is None or len(self.caps) != len(pads):
+            self._learn(pads)
+        caps, nch = self.caps, len(pads)
+        ft0 = pads[0][1]
+        C, dev = int(ft0.shape[1]), ft0.device
+        hdr_rows = (nch + C - 1) // C
+        rows = hdr_rows + sum(caps)
+        i = self.k % 2
+        self.k += 1
+        cuda = ft0.is_cuda
+        if cuda:
+            main = torch.cuda.current_stream()
+            if self.comm is None:
+                self.comm = torch.cuda.Stream(device=dev)
+            if self.done[i] is not None:
+                main.wait_event(self.done[i])  # the exchange two steps back has read this staging buffer
+        if self.stage[i] is None or self.stage[i].shape[0] != rows:
+            self.stage[i] = torch.zeros((rows, C), dtype=ft0.dtype, device=dev)
+            want = self.all_ranks or rank == self.root
+            self.recv[i] = torch.empty((world, rows, C), dtype=ft0.dtype, device=dev) if want else None
+        st, rv = self.stage[i], self.recv[i]
+        hdr = st[:hdr_rows].view(-1)
+        at = hdr_rows
+        for j, ((off, ft), cap) in enumerate(zip(pads, caps)):
+            hdr[j : j + 1].copy_(off[-1:])  # int32 -> float64, exact
+            st[at : at + cap].copy_(ft[:cap])
+            at += cap
+
+        def exchange():
+            if world == 1:
+                rv[0].copy_(st)
+            elif self.all_ranks:
+                dist.all_gather_into_tensor(rv.view(world * rows, C), st, group=self.group)
             else:
-                counts = n_local
-            self.cap = min(max(int(int(counts.max().item()) * 1.25) + 1, 16), ftable.shape[0])
-            self.stage = None
-        cap, C = self.cap, ftable.shape[1]
+                dist.gather(st, [rv[r] for r in range(world)] if rank == self.root else None, dst=dist.get_global_rank(self.group, self.root) if self.group is not None else self.root, group=self.group)
 
-        def redo():
-            self.cap = 0
-            return gather_tables_padded(ftable, offsets, self.group)
+        ready = None
+        if cuda:
+            staged = torch.cuda.Event()
+            staged.record(main)
+            with torch.cuda.stream(self.comm):
+                self.comm.wait_event(staged)
+                exchange()
+                ready = torch.cuda.Event()
+                ready.record(self.comm)
+            self.done[i] = ready
+        else:
+            exchange()
+        return GatheredTable(self, rv, list(caps), hdr_rows, [int(ft.shape[0]) for _, ft in pads], ready)
 
-        def exchange(rows, n):
-            counts = torch.empty(world, dtype=torch.int64, device=ftable.device)
-            flat = torch.empty((world * cap, C), dtype=ftable.dtype, device=ftable.device)
-            if world > 1:
-                dist.all_gather_into_tensor(counts, n, group=self.group)
-                dist.all_gather_into_tensor(flat, rows, group=self.group)
-            else:
-                counts.copy_(n)
-                flat.copy_(rows)
-            return flat.view(world, cap, C), counts
-
-        if not ftable.is_cuda:
-            parts, counts = exchange(ftable[:cap].contiguous(), n_local)
-            return GatheredTable(parts, counts, cap, redo)
-        main = torch.cuda.current_stream()
-        if self.comm is None:
-            self.comm = torch.cuda.Stream(device=ftable.device)
-        if self.stage is None:
-            self.stage = torch.empty((cap, C), dtype=ftable.dtype, device=ftable.device)
-            self.stage_n = torch.empty(1, dtype=torch.int64, device=ftable.device)
-        if self.done is not None:
-            main.wait_event(self.done)  # the previous exchange has read the staging buffers
-        self.stage.copy_(ftable[:cap])
-        self.stage_n.copy_(n_local)
-        staged = torch.cuda.Event()
-        staged.record(main)
-        with torch.cuda.stream(self.comm):
-            self.comm.wait_event(staged)
-            parts, counts = exchange(self.stage, self.stage_n)
-            self.done = torch.cuda.Event()
-            self.done.record(self.comm)
-        return GatheredTable(parts, counts, cap, redo, ready=self.done)
+    __call__ = gather
 
 
 def segment_zstack_sharded(stack_local, z0, group=None, **kwargs):

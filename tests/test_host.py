@@ -98,16 +98,38 @@ padded[: local.shape[0]] = local
 offsets = torch.tensor([0, local.shape[0]], dtype=torch.int32)
 out2 = pdist.gather_tables_padded(padded, offsets)
 assert out2.shape == full.shape and np.array_equal(out2.numpy(), full), (rank, out2.shape)
-# sync-free gather: capacity learnt on first use, then speculative; a larger table later forces the redo path
-tg = pdist.TableGather()
-for _ in range(2):
-    out3 = tg(padded, offsets).compact()
-    assert np.array_equal(out3.numpy(), full), rank
-assert 0 < tg.cap < cap
+# sync-free gather of a whole step (two chunks) in one collective: capacity learnt on first use, then speculative
+cut = local.shape[0] // 2
+padA = torch.full((cap, 13), -7.0, dtype=torch.float64); padA[:cut] = local[:cut]
+padB = torch.full((cap, 13), -7.0, dtype=torch.float64); padB[: local.shape[0] - cut] = local[cut:]
+pads = [(torch.tensor([0, cut], dtype=torch.int32), padA), (torch.tensor([0, local.shape[0] - cut], dtype=torch.int32), padB)]
+tg = pdist.TableGather()                      # gather to rank 0
+ta = pdist.TableGather(all_ranks=True)        # all-gather form
+for _ in range(3):                            # three steps: both staging buffers get reused
+    out3 = tg(pads).compact()
+    assert (out3 is None) if rank != 0 else np.array_equal(out3.numpy(), full), rank
+    assert np.array_equal(ta(pads).compact().numpy(), full), rank
+assert all(0 < c < cap for c in tg.caps)
+# a later, larger table: the exchange raises (its staged copy is truncated) and enlarges the capacity for the next one
 grown = torch.full((cap, 13), -7.0, dtype=torch.float64)
 grown[: cap - 1] = torch.arange((cap - 1) * 13, dtype=torch.float64).view(cap - 1, 13) + 1000 * rank
-out4 = tg(grown, torch.tensor([0, cap - 1], dtype=torch.int32)).compact()   # cap - 1 rows > the learnt capacity
-assert out4.shape == (2 * (cap - 1), 13) and out4[cap - 1, 0].item() == 1000.0 and out4[0, 0].item() == 0.0
+gp = [(torch.tensor([0, cap - 1], dtype=torch.int32), grown), pads[1]]
+try:
+    ta(gp).compact()
+    raise SystemExit("overflow not detected")
+except Exception as e:
+    assert "capacity" in str(e), e
+out4 = ta(gp).compact()
+nBs = [None] * world
+dist.all_gather_object(nBs, int(local.shape[0] - cut))
+assert out4.shape == (world * (cap - 1) + sum(nBs), 13), out4.shape
+assert out4[0, 0].item() == 0.0 and out4[cap - 1 + nBs[0], 0].item() == 1000.0   # rank 1's rows follow rank 0's two chunks
+# a count above the TABLE capacity is an error of its own (silent truncation otherwise)
+try:
+    pdist.gather_tables_padded(padded, torch.tensor([0, cap + 5], dtype=torch.int32))
+    raise SystemExit("table overflow not detected")
+except Exception as e:
+    assert "overflow" in str(e), e
 empty = pdist.gather_tables(torch.zeros((0, 13), dtype=torch.float64) if rank == 1 else local)
 assert empty.shape[0] == local.shape[0] * (1 if rank == 0 else 0) + (0 if rank == 1 else 0) or True
 dist.barrier()
