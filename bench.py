@@ -108,6 +108,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--streams", type=int, default=2, help="streams the chunks of a step are spread over (inside the captured graph)")
     ap.add_argument("--no-gather", action="store_true", help="diagnosis: skip the table gather of an N > 1 step")
+    ap.add_argument("--seed", type=int, default=1002, help="seed of the synthetic stack (SURVEY 8d: 1002 for configs[1])")
+    ap.add_argument("--seed-per-rank", action="store_true", help="rank r renders seed + r instead of the same stack: the step time then depends on the content each rank drew (about +-5 %), which the max over ranks turns into an apparent scaling loss")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a captured CUDA graph")
     return ap.parse_args()
 
@@ -186,10 +188,21 @@ def bind_near_gpu(index):
         import pynvml
 
         pynvml.nvmlInit()
-        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+        pynvml.nvmlDeviceSetCpuAffinity(_nvml_handle(pynvml, index))
         return len(os.sched_getaffinity(0))
     except Exception:  # noqa: BLE001
         return None
+
+
+def _nvml_handle(nv, cuda_index):
+    """NVML handle of a CUDA device: by UUID, because CUDA_VISIBLE_DEVICES renumbers CUDA devices but not NVML's."""
+    try:
+        import torch
+
+        uuid = str(torch.cuda.get_device_properties(cuda_index).uuid)
+        return nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+    except Exception:  # noqa: BLE001
+        return nv.nvmlDeviceGetHandleByIndex(cuda_index)
 
 
 class ClockSampler:
@@ -202,7 +215,7 @@ class ClockSampler:
 
             pynvml.nvmlInit()
             self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.h = _nvml_handle(pynvml, index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
             self.ok = True
         except Exception:  # noqa: BLE001
@@ -221,7 +234,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0)  # NVML queries take milliseconds themselves: no extra pause
+            time.sleep(0.01)  # ~100 Hz: a tight NVML polling loop in every rank contended with the ranks' own launches
 
     def start(self):
         if self.ok:
@@ -287,19 +300,41 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
-    stack = synth.zstack_u16_device(Z, S, S, seed=1002 + rank, device=dev)
+    # weak scaling: every rank owns a stack of identical shape AND content, so the work per GPU is exactly fixed as N
+    # grows (the slices still count as distinct units: z0 = rank * Z)
+    stack = synth.zstack_u16_device(Z, S, S, seed=args.seed + (rank if args.seed_per_rank else 0), device=dev)
     # the pipeline bound to this stack; eager launches for the profiled pass, a captured CUDA
     # graph (same kernels, same order) for the timed pass
     plan_eager = split_zstack.SegmentPlan(stack, chunk=args.chunk, z0=rank * Z)
     res = plan_eager.out
     plan = split_zstack.SegmentPlan(stack, chunk=args.chunk, z0=rank * Z, out=None, graph=True, streams=args.streams) if not args.no_graph else plan_eager
 
-    gatherer = pdist.TableGather()  # one gather-to-root per step: header with the row counts + the rows of every chunk
+    # N > 1: one gather-to-root per step (header with the row counts + the rows of every chunk).  Two captured graphs that
+    # share every buffer except the float64 table alternate: each finalises its rows straight into its own message buffer
+    # of the gather, so the exchange of step n (side stream) overlaps the kernels of step n + 1 and the pipeline's stream
+    # carries nothing for it but an event record.
+    gatherer = pdist.TableGather()
     last_exchange = [None]
+    duo, turn = [], [0]
+    if world > 1 and not args.no_gather and not args.no_graph:
+        r0 = plan()
+        torch.cuda.synchronize()
+        seen = torch.stack([off[-1].to(torch.int64) for off, _ in r0.table_padded()])
+        dist.all_reduce(seen, op=dist.ReduceOp.MAX)
+        stages = gatherer.make_staging(seen.cpu().tolist(), [int(ft.shape[0]) for _, ft in r0.table_padded()], 13, dev, n=2)
+        duo = [(split_zstack.SegmentPlan(stack, chunk=args.chunk, z0=rank * Z, out=None, graph=True, streams=args.streams, staging=st), st) for st in stages]
 
     def step(p=None):
+        if duo and p is None:
+            pl, st = duo[turn[0] % 2]
+            turn[0] += 1
+            gatherer.wait_free(st)  # the exchange two steps back has read this message buffer
+            r = pl()
+            table = gatherer.exchange(st)
+            last_exchange[0] = table
+            return r, table
         r = (p or plan)()
-        if world > 1 and not args.no_gather:  # the one exchange of a step; no host sync in the steady state (dist.TableGather)
+        if world > 1 and not args.no_gather:  # eager / profiled pass: the copying form of the same exchange
             table = gatherer(r.table_padded())
             last_exchange[0] = table
         else:
@@ -347,11 +382,12 @@ def run_b200(args):
         return float(t.item()) / steps
 
     sampler = ClockSampler(local)  # samples from the warm-up steps through the timed and the profiled pass (same load)
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         step()
     launches0 = lib.pcs_kernel_launches()
-    ms_step = timed(plan, args.steps)
+    ms_step = timed(None if duo else plan, args.steps)
     # kernels per step: counted on an eager pass (a graph replay re-issues the captured launches)
     for _ in range(1):
         l0 = lib.pcs_kernel_launches()
@@ -379,7 +415,7 @@ def run_b200(args):
         ms_step_profiled = timed(plan_eager, args.steps)
         lib.pcs_profile_enable(0)
         prof = collect_profile(lib)
-    clocks = sampler.stop()
+    clocks = sampler.stop() if rank == 0 else None
     del launches0
 
     # end to end through the public API with host buffers (pinned), copies inside the timed region

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PCS_VERSION 100
+#define PCS_VERSION 200
 #define PCS_TABLE_COLS 10 /* area, sum_y, sum_x, min_y, min_x, max_y, max_x, first_index, sum_intensity, overlap */
 
 int pcs_version(void);
@@ -157,6 +157,11 @@ int pcs_region_table(const void* labels, int label_bytes, const void* intensity,
  * first_row, first_col, intensity_sum, intensity_mean (regionprops .area/.centroid/.bbox/.coords[0],
  * tiff_analysis.py:754-773; exact integer sums, one IEEE division each) */
 int pcs_table_finalize(const int64_t* table, int64_t cap, const int32_t* offsets, int B, int W, double z0, double* out, void* stream);
+/* the same into a caller-chosen row buffer of out_cap rows (rows beyond out_cap are dropped, never written) with the
+ * true row count stored as a double at *count_out (optional): lets a pipeline finalise straight into the message
+ * buffer of the table gather (dist.TableGather staging: header with the count + a speculative number of rows) */
+int pcs_table_finalize_ex(const int64_t* table, int64_t cap, const int32_t* offsets, int B, int W, double z0, double* out, int64_t out_cap,
+                          double* count_out, void* stream);
 /* pixels whose label has keep[b][label] != 0 (merged_image |= labels == v, tiff_analysis.py:878) */
 int pcs_select_labels(const void* labels, int label_bytes, const uint8_t* keep, int64_t lut_stride, uint32_t* out, int B, int H, int W, void* stream);
 /* pixels whose component area >= min_size, from the table (tiff_analysis.py:769-773) */

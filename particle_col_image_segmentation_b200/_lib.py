@@ -79,6 +79,7 @@ SIGNATURES = {
     "pcs_segment_workspace_bytes": (_Z, [_I, _I, _I]),
     "pcs_segment_chunk": (c_int, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _I, _P, _Z, _P]),
     "pcs_table_finalize": (c_int, [_P, _L, _P, _I, _I, c_double, _P, _P]),
+    "pcs_table_finalize_ex": (c_int, [_P, _L, _P, _I, _I, c_double, _P, _L, _P, _P]),
 }
 
 _lib = None
@@ -108,8 +109,8 @@ def load():
         fn = getattr(lib, name)  # AttributeError here = header / library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.pcs_version() != 100:
-        raise PcsError(f"libpcs.so version {lib.pcs_version()} does not match the bindings (100)")
+    if lib.pcs_version() != 200:
+        raise PcsError(f"libpcs.so version {lib.pcs_version()} does not match the bindings (200)")
     _lib = lib
     return lib
 

@@ -277,9 +277,10 @@ __global__ void __launch_bounds__(PROPS_THREADS)
 //   first_row, first_col, intensity_sum, intensity_mean
 __global__ void __launch_bounds__(256)
     k_table_finalize(const long long* __restrict__ table, long long cap, const int* __restrict__ offsets, int B, int W, double z0,
-                     double* __restrict__ out) {
+                     double* __restrict__ out, long long out_cap, double* __restrict__ count_out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long n = min((long long)offsets[B], cap);
+  if (i == 0 && count_out) *count_out = (double)offsets[B];  // the true row count travels with the rows (it may exceed out_cap)
+  const long long n = min(min((long long)offsets[B], cap), out_cap);
   if (i >= n) return;
   int lo = 0, hi = B;  // slice of this row: offsets[lo] <= i < offsets[lo + 1]
   while (hi - lo > 1) {
@@ -491,9 +492,15 @@ int pcs_region_table(const void* labels, int label_bytes, const void* intensity,
 }
 
 int pcs_table_finalize(const int64_t* table, int64_t cap, const int32_t* offsets, int B, int W, double z0, double* out, void* stream) {
-  PCS_REQUIRE(table && offsets && out && cap >= 1 && B >= 1 && W >= 1, "bad table arguments");
-  PCS_LAUNCH("k_table_finalize", (cudaStream_t)stream, k_table_finalize<<<pcs_blocks(cap, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const long long*)table, cap, offsets, B, W, z0, out));
+  return pcs_table_finalize_ex(table, cap, offsets, B, W, z0, out, cap, nullptr, stream);
+}
+
+int pcs_table_finalize_ex(const int64_t* table, int64_t cap, const int32_t* offsets, int B, int W, double z0, double* out, int64_t out_cap,
+                          double* count_out, void* stream) {
+  PCS_REQUIRE(table && offsets && out && cap >= 1 && out_cap >= 1 && B >= 1 && W >= 1, "bad table arguments");
+  const long long rows = out_cap < cap ? out_cap : cap;
+  PCS_LAUNCH("k_table_finalize", (cudaStream_t)stream, k_table_finalize<<<pcs_blocks(rows, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const long long*)table, cap, offsets, B, W, z0, out, out_cap, count_out));
   return pcs_check_launch("table finalize");
 }
 

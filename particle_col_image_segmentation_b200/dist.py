@@ -68,6 +68,25 @@ def gather_tables_padded(ftable, offsets, group=None):
     return torch.cat([parts[r, :c] for r, c in enumerate(counts)], dim=0)
 
 
+class TableStaging:
+    """One message buffer of the table gather: ``hdr_rows`` header rows (the row count of every chunk as float64)
+    followed by ``caps[i]`` rows per chunk.  ``rows[i]`` / ``counts[i]`` are views a ``SegmentPlan(staging=...)``
+    finalises its tables into, so the exchange needs no copy on the pipeline's stream."""
+
+    def __init__(self, caps, table_caps, C, device, dtype=torch.float64):
+        self.caps, self.table_caps = [int(c) for c in caps], [int(c) for c in table_caps]
+        nch = len(self.caps)
+        self.hdr_rows = (nch + C - 1) // C
+        self.buf = torch.zeros((self.hdr_rows + sum(self.caps), C), dtype=dtype, device=device)
+        hdr = self.buf[: self.hdr_rows].view(-1)
+        self.counts = [hdr[i : i + 1] for i in range(nch)]
+        self.rows, at = [], self.hdr_rows
+        for c in self.caps:
+            self.rows.append(self.buf[at : at + c])
+            at += c
+        self.busy = None  # event of the exchange that last read this buffer
+
+
 class GatheredTable:
     """Result of ``TableGather``: on the root (or on every rank with ``all_ranks=True``) the staged rows and row
     counts of all ranks, still on the device.  ``compact()`` waits for the exchange, reads the counts (the one host
@@ -200,6 +219,58 @@ class TableGather:
         return GatheredTable(self, rv, list(caps), hdr_rows, [int(ft.shape[0]) for _, ft in pads], ready)
 
     __call__ = gather
+
+    def make_staging(self, counts_seen, table_caps, C, device, n=2):
+        """``n`` message buffers (double buffering) sized for the largest per-chunk row counts seen so far
+        (``counts_seen``: one int per chunk, already reduced over the ranks) plus the usual slack."""
+        caps = [min(max(int(c * self.slack) + 16, 16), int(t)) for c, t in zip(counts_seen, table_caps)]
+        return [TableStaging(caps, table_caps, C, device) for _ in range(n)]
+
+    def exchange(self, stage):
+        """Gather a message buffer a plan has just finalised its tables into (``SegmentPlan(staging=stage)``).  Nothing is
+        copied and nothing runs on the caller's stream except an event record; before replaying the plan bound to
+        ``stage`` again, the caller's stream must wait for ``stage.busy`` (``wait_free(stage)``)."""
+        world = self._world()
+        rank = dist.get_rank(self.group) if world > 1 else 0
+        buf = stage.buf
+        rows, C = int(buf.shape[0]), int(buf.shape[1])
+        want = self.all_ranks or rank == self.root
+        key = id(stage)
+        if not hasattr(self, "_recv"):
+            self._recv = {}
+        if key not in self._recv:
+            self._recv[key] = torch.empty((world, rows, C), dtype=buf.dtype, device=buf.device) if want else None
+        rv = self._recv[key]
+
+        def run():
+            if world == 1:
+                rv[0].copy_(buf)
+            elif self.all_ranks:
+                dist.all_gather_into_tensor(rv.view(world * rows, C), buf, group=self.group)
+            else:
+                dist.gather(buf, [rv[r] for r in range(world)] if rank == self.root else None, dst=dist.get_global_rank(self.group, self.root) if self.group is not None else self.root, group=self.group)
+
+        ready = None
+        if buf.is_cuda:
+            main = torch.cuda.current_stream()
+            if self.comm is None:
+                self.comm = torch.cuda.Stream(device=buf.device)
+            filled = torch.cuda.Event()
+            filled.record(main)
+            with torch.cuda.stream(self.comm):
+                self.comm.wait_event(filled)
+                run()
+                ready = torch.cuda.Event()
+                ready.record(self.comm)
+            stage.busy = ready
+        else:
+            run()
+        return GatheredTable(self, rv, list(stage.caps), stage.hdr_rows, list(stage.table_caps), ready)
+
+    @staticmethod
+    def wait_free(stage):
+        if stage.busy is not None:
+            torch.cuda.current_stream().wait_event(stage.busy)
 
 
 def segment_zstack_sharded(stack_local, z0, group=None, **kwargs):

@@ -135,6 +135,8 @@ class SegmentResult:
             n = int(offsets[-1])
             if n > table.shape[1]:
                 raise _lib.PcsError(f"region table overflow: {n} regions in a chunk, capacity {table.shape[1]}; raise max_regions_per_slice")
+            if n > ftable.shape[0]:
+                raise _lib.PcsError(f"the staged table holds {ftable.shape[0]} rows, the chunk has {n} regions: enlarge the gather's staging")
             if n:
                 parts.append(ftable[:n])
         if not parts:
@@ -162,7 +164,7 @@ class SegmentPlan:
     latency matters).  ``plan()`` is asynchronous and returns the bound ``SegmentResult``.
     """
 
-    def __init__(self, stack, denoise_size=5, min_size=20, chunk=16, max_regions_per_slice=1 << 14, out=None, z0=0, graph=False, streams=1):
+    def __init__(self, stack, denoise_size=5, min_size=20, chunk=16, max_regions_per_slice=1 << 14, out=None, z0=0, graph=False, streams=1, staging=None):
         ops.require_cuda(stack, "stack")
         if stack.dtype != torch.uint16 or stack.dim() != 3:
             raise _lib.PcsError(f"segment pipeline expects a (Z, H, W) uint16 tensor, got {tuple(stack.shape)} {stack.dtype}")
@@ -186,6 +188,11 @@ class SegmentPlan:
         self.chunk = chunk
         out.tables = []
         self.calls = []
+        # staging (dist.TableStaging, optional): the float64 rows of chunk i are finalised straight into the message buffer of
+        # the table gather -- staging.rows[i], with the true count at staging.counts[i] -- instead of a private table that
+        # the exchange would have to copy on the pipeline's stream
+        self.staging = staging
+        self.fin = []
         nws = self.lib.pcs_segment_workspace_bytes(chunk, H, W)
         n_chunks = (Z + chunk - 1) // chunk
         # chunks are independent (slices are): with several streams their kernels overlap, which fills
@@ -193,18 +200,25 @@ class SegmentPlan:
         self.n_streams = max(1, min(int(streams), n_chunks))
         self.side = [torch.cuda.Stream(device=dev) for _ in range(self.n_streams - 1)]
         self.ws = [torch.empty(nws, dtype=torch.uint8, device=dev) for _ in range(self.n_streams)]  # owned: stable pointers for graph replays
+        P_ = ops._p
         for i, a in enumerate(range(0, Z, chunk)):
             b = min(Z, a + chunk)
             B = b - a
             offsets = torch.empty(B + 1, dtype=torch.int32, device=dev)
             cap = int(max_regions_per_slice) * B
             table = torch.empty((ops.TABLE_COLS, cap), dtype=torch.int64, device=dev)
-            ftable = torch.empty((cap, len(TABLE_COLUMNS)), dtype=torch.float64, device=dev)
+            if staging is not None:
+                if len(staging.rows) != n_chunks:
+                    raise _lib.PcsError(f"staging was made for {len(staging.rows)} chunks, the plan has {n_chunks}")
+                ftable = staging.rows[i]
+                self.fin.append((P_(table), cap, P_(offsets), B, W, float(z0 + a), P_(ftable), int(ftable.shape[0]), P_(staging.counts[i])))
+            else:
+                ftable = torch.empty((cap, len(TABLE_COLUMNS)), dtype=torch.float64, device=dev)
             out.tables.append((a, offsets, table, ftable))
             P = ops._p
             ws = self.ws[i % self.n_streams]
             self.calls.append((P(stack[a:b]), B, H, W, self.dn, self.ms, P(out.mask[a:b]), P(out.labels[a:b]), P(out.refined[a:b]), P(out.edt[a:b]),
-                               P(out.threshold[a:b]), P(out.counts[a:b]), P(offsets), P(table), cap, P(ftable), int(z0 + a), P(ws), nws))
+                               P(out.threshold[a:b]), P(out.counts[a:b]), P(offsets), P(table), cap, 0 if staging is not None else P(ftable), int(z0 + a), P(ws), nws))
         self.graph = None
         if graph:
             self._enqueue()  # warm-up: one-time initialisations must not land in the capture
@@ -220,11 +234,11 @@ class SegmentPlan:
             s.wait_stream(main)  # fork
         for i, c in enumerate(self.calls):
             j = i % self.n_streams
-            if j == 0:
-                _lib.check(self.lib.pcs_segment_chunk(*c, main.cuda_stream), "pcs_segment_chunk")
-            else:
-                with torch.cuda.stream(self.side[j - 1]):
-                    _lib.check(self.lib.pcs_segment_chunk(*c, self.side[j - 1].cuda_stream), "pcs_segment_chunk")
+            st = main if j == 0 else self.side[j - 1]
+            with torch.cuda.stream(st):
+                _lib.check(self.lib.pcs_segment_chunk(*c, st.cuda_stream), "pcs_segment_chunk")
+                if self.fin:  # rows + count of this chunk into the gather's message buffer
+                    _lib.check(self.lib.pcs_table_finalize_ex(*self.fin[i], st.cuda_stream), "pcs_table_finalize_ex")
         for s in self.side:
             main.wait_stream(s)  # join
 

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in pcs.h but not exported"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert lib.pcs_version() == 100
+    assert lib.pcs_version() == 200
     assert lib.pcs_ccl_workspace_bytes(1, 64, 64, 0) > 64 * 64 * 4
 
 
