@@ -108,6 +108,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--streams", type=int, default=2, help="streams the chunks of a step are spread over (inside the captured graph)")
     ap.add_argument("--no-gather", action="store_true", help="diagnosis: skip the table gather of an N > 1 step")
+    ap.add_argument("--workload", default="zstack64", choices=["zstack64", "zstack256", "refine4096", "class2048", "nanosims"],
+                    help="zstack64 = BASELINE.json configs[1] (the default line); the others: bench_workloads.py")
     ap.add_argument("--seed", type=int, default=1002, help="seed of the synthetic stack (SURVEY 8d: 1002 for configs[1])")
     ap.add_argument("--seed-per-rank", action="store_true", help="rank r renders seed + r instead of the same stack: the step time then depends on the content each rank drew (about +-5 %), which the max over ranks turns into an apparent scaling loss")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a captured CUDA graph")
@@ -505,6 +507,14 @@ def run_b200(args):
 
 def main():
     args = parse()
+    if args.workload == "zstack256":
+        args.slices = 256  # the north_star's own target; same pipeline, same line
+    elif args.workload != "zstack64" and args.impl != "reference":
+        if int(os.environ.get("RANK", "0")) == 0:
+            import bench_workloads
+
+            bench_workloads.run(args, sys.modules[__name__])
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

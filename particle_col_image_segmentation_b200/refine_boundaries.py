@@ -13,7 +13,7 @@ import torch
 from . import _io, ops
 
 
-def refine_boundaries(boundary_map, threshold=0.5, run_watershed=False):
+def refine_boundaries(boundary_map, threshold=0.5, run_watershed=False, return_sweeps=False):
     """-> dict(binary_mask bool, distance float64, local_max bool, markers int32[, labels int32]).
 
     ``binary_mask = boundary_map < threshold``            refine_boundaries.py:44-45
@@ -46,6 +46,8 @@ def refine_boundaries(boundary_map, threshold=0.5, run_watershed=False):
     if run_watershed:
         from . import segmentation
 
-        lab = segmentation.watershed(t[0], markers[0], mask=ops.unpack(bits, W, torch.bool)[0])
+        lab, sweeps = segmentation.watershed(t[0], markers[0], mask=ops.unpack(bits, W, torch.bool)[0], return_sweeps=True)
         out["labels"] = _io.back(lab, np_in)
+        if return_sweeps:
+            out["sweeps"] = sweeps  # relaxation sweeps the flood took (diagnostic; not a reference output)
     return out
