@@ -5,7 +5,7 @@ TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  Each function cites the
 pass over a per-label table instead of the reference's per-region Python loops)
 but returns the same structures, so it can be compared entry by entry with the
 reference module loaded through ``oracle.ref_loader`` (done in
-``tests/test_oracle_vs_reference.py`` and frozen in ``tests/golden``).
+``tests/test_oracle.py::test_l2_matches_live_reference`` and frozen in ``tests/golden``).
 """
 
 import numpy as np

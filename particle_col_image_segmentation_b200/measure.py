@@ -47,7 +47,22 @@ def label(label_image, background=None, return_num=False, connectivity=None):
     return (out, int(counts[0].item())) if return_num else out
 
 
-_HOST_CACHE = {}
+class LabelHolder:
+    """The label image a batch of ``RegionProperties`` was measured on.  Regions made by one ``regionprops`` /
+    ``get_cell_positions_and_areas`` call share one holder, and the holder fetches a device image to the host at
+    most once.  (A cache keyed by ``data_ptr`` served pixels of a freed image whenever the allocator handed its
+    address to the next one.)"""
+
+    __slots__ = ("image", "_host")
+
+    def __init__(self, image):
+        self.image, self._host = image, None
+
+    def host(self):
+        if self._host is None:
+            li = self.image
+            self._host = li.cpu().numpy() if isinstance(li, torch.Tensor) else np.asarray(li)
+        return self._host
 
 
 class RegionProperties:
@@ -56,7 +71,7 @@ class RegionProperties:
     def __init__(self, label, row, label_image, intensity_image, shape):
         self.label = int(label)
         self._row = row
-        self._label_image = label_image
+        self._label_image = label_image if isinstance(label_image, LabelHolder) else LabelHolder(label_image)
         self._intensity_image = intensity_image
         self._shape = shape
 
@@ -89,13 +104,7 @@ class RegionProperties:
         return divmod(int(self._row[ops.T_FIRST]), self._shape[1])
 
     def _host_labels(self):
-        li = self._label_image
-        if isinstance(li, torch.Tensor):  # device labels: fetch once, share between regions
-            key = (li.data_ptr(), tuple(li.shape))
-            if _HOST_CACHE.get("key") != key:
-                _HOST_CACHE["key"], _HOST_CACHE["arr"] = key, li.cpu().numpy()
-            return _HOST_CACHE["arr"]
-        return np.asarray(li)
+        return self._label_image.host()  # device labels: fetched once, shared between the regions of one call
 
     @property
     def image(self):
@@ -163,9 +172,5 @@ def regionprops(label_image, intensity_image=None, cache=True, *, overlap_mask=N
         raise TypeError("Only 2-D images supported.")
     tab, n = region_table_host(label_image, intensity_image, overlap_mask, n_labels)
     shape = tuple(label_image.shape)
-    regions = []
-    for i in range(n):
-        if tab[ops.T_AREA, i] <= 0:
-            continue
-        regions.append(RegionProperties(i + 1, tab[:, i], label_image, intensity_image, shape))
-    return regions
+    holder = LabelHolder(label_image)
+    return [RegionProperties(i + 1, tab[:, i], holder, intensity_image, shape) for i in np.flatnonzero(tab[ops.T_AREA, :n] > 0).tolist()]

@@ -25,7 +25,7 @@ import numpy as np
 import torch
 
 from . import _io, ops
-from .measure import RegionProperties
+from .measure import LabelHolder, RegionProperties
 from .morphology import disk
 from .ndimage import median_filter  # noqa: F401  (tiff_analysis.py:42)
 
@@ -73,10 +73,6 @@ def _u8_image(a):
     return t
 
 
-def _regions_from_table(tab, n, label_image, shape):
-    return [RegionProperties(i + 1, tab[:, i], label_image, None, shape) for i in range(n) if tab[ops.T_AREA, i] > 0]
-
-
 def _label_and_table(t, bits=None):
     """Label a (1, H, W) uint8 class image (multi-valued) or a bit image; return
     ``(labels, n, host table, class value per label)``."""
@@ -93,29 +89,40 @@ def _label_and_table(t, bits=None):
 
 # ---------------------------------------------------------------- L2 functions
 def get_cell_positions_and_areas(z_slice, cell_types, merged=False):
-    """tiff_analysis.py:742-789: ``(cell_pos, cell_clusters, particle_area, merged_clusters)``."""
+    """tiff_analysis.py:742-789: ``(cell_pos, cell_clusters, particle_area, merged_clusters)``.
+
+    The reference walks every connected component in Python -- label noise included, tens of thousands of one-pixel
+    specks on an ilastik image -- and asks each for its class, area and size bracket.  Here those are array passes
+    over the per-label table (one D2H copy); region objects are created only for the components that survive the
+    area filters.  Dict keys keep the reference's insertion order (a cell type enters both dicts when its first
+    component of ANY size is met)."""
     t = _u8_image(z_slice)
     shape = (int(t.shape[1]), int(t.shape[2]))
     labels, n, tab, cls = _label_and_table(t)
-    label_image = labels[0]
+    holder = LabelHolder(labels[0])
+    area = tab[ops.T_AREA, :n]
+    # class value -> cell type name, once per distinct value (a value missing from cell_types raises KeyError, as :756 does)
+    values, first_at, inv = np.unique(cls[:n], return_index=True, return_inverse=True)
+    names = [cell_types[int(v)] for v in values]
     cell_pos, cell_clusters = {}, {}
     particle_area = 0
-    for i in range(n):
-        region = RegionProperties(i + 1, tab[:, i], label_image, None, shape)
-        cell_type = cell_types[int(cls[i])]
+    is_particle = np.array([nm == "Particle" for nm in names], dtype=bool)
+    if n and is_particle[inv].any():
+        particle_area = np.float64(area[is_particle[inv]].sum())  # integer areas: any summation order is exact
+    for vi in np.argsort(first_at, kind="stable").tolist():  # cell types in order of their first component
+        cell_type = names[vi]
         if cell_type not in CELL_TYPES:
-            if cell_type == "Particle":
-                particle_area += region.area
             continue
-        min_cell_area = MIN_CELL_AREA[cell_type]
-        min_cluster_area = MIN_CLUSTER_AREA[cell_type]
+        of_type = inv == vi
         if cell_type not in cell_pos:
             cell_pos[cell_type] = []
             cell_clusters[cell_type] = []
-        if region.area >= min_cell_area and region.area < min_cluster_area:
-            cell_pos[cell_type].append(region)
-        if region.area >= min_cluster_area:
-            cell_clusters[cell_type].append(region)
+        lo, hi = MIN_CELL_AREA[cell_type], MIN_CLUSTER_AREA[cell_type]
+        cells = np.flatnonzero(of_type & (area >= lo) & (area < hi))
+        clusters = np.flatnonzero(of_type & (area >= hi))
+        # two class values may map to one cell type: keep label order within the type
+        cell_pos[cell_type] = _merge_by_label(cell_pos[cell_type], [RegionProperties(i + 1, tab[:, i], holder, None, shape) for i in cells.tolist()])
+        cell_clusters[cell_type] = _merge_by_label(cell_clusters[cell_type], [RegionProperties(i + 1, tab[:, i], holder, None, shape) for i in clusters.tolist()])
     cell_area_averages = {}
     for cell_type, cell_array in cell_pos.items():
         cell_area_averages[cell_type] = np.average([cell.area for cell in cell_array])
@@ -127,6 +134,12 @@ def get_cell_positions_and_areas(z_slice, cell_types, merged=False):
     else:
         merged_clusters = {}
     return cell_pos, cell_clusters, particle_area, merged_clusters
+
+
+def _merge_by_label(a, b):
+    if not a:
+        return b
+    return sorted(a + b, key=lambda r: r.label)
 
 
 def _clusters_from_distances(t, cell_pos, cell_clusters, cell_types, want_numpy=True):
@@ -156,24 +169,57 @@ def get_cell_clusters_from_distances(z_slice, cell_pos, cell_clusters, cell_type
 
 
 def _merged_regions(bits, t, og_cell_regions, want_numpy=True):
+    """tiff_analysis.py:826-883.  The reference groups the regions under each dilated component with a nested Python
+    loop (O(R^2)) and ORs one full-image ``dilated_labels == v`` per group; here the group-by is one pass over the
+    keys (``np.unique`` + unbuffered ``ufunc.at``, which adds in list order like ``np.average`` over the rows does,
+    so the area-weighted centroids come out bit-identical) and the selected components are one label-LUT kernel."""
     H, W = int(t.shape[1]), int(t.shape[2])
     dilated = ops.dilate(bits, W, disk(CELL_CLUSTER_DISTANCE_THRESHOLD // 2))
     dlabels, dcounts, _ = ops.label_bits(dilated, W, connectivity=8, dtype=torch.int32)
     merged_regions = []
-    keys = []
-    if og_cell_regions:
-        cents = [r.centroid for r in og_cell_regions]
-        lin = np.array([int(cy) * W + int(cx) for cy, cx in cents], dtype=np.int64)
-        keys = ops.gather(dlabels, None, torch.from_numpy(lin).to(t.device)).cpu().numpy().tolist()
     processed = []
-    for k in keys:
-        if k > 0 and k not in processed:
-            touching = [r for r, kk in zip(og_cell_regions, keys) if kk == k]
-            combined_area = sum(r.area for r in touching)
-            combined_centroid = np.average([r.centroid for r in touching], axis=0, weights=[r.area for r in touching])
-            bbox = (min(r.bbox[0] for r in touching), min(r.bbox[1] for r in touching), max(r.bbox[2] for r in touching), max(r.bbox[3] for r in touching))
-            merged_regions.append({"area": combined_area, "centroid": combined_centroid, "regions": touching, "bbox": bbox})
-            processed.append(k)
+    if og_cell_regions:
+        R = len(og_cell_regions)
+        rows = np.stack([r._row for r in og_cell_regions]) if all(hasattr(r, "_row") for r in og_cell_regions) else None
+        if rows is not None:
+            area = rows[:, ops.T_AREA].astype(np.float64)
+            cent = np.column_stack([rows[:, ops.T_SUMY] / area, rows[:, ops.T_SUMX] / area])
+            bbox = np.column_stack([rows[:, ops.T_MINY], rows[:, ops.T_MINX], rows[:, ops.T_MAXY] + 1, rows[:, ops.T_MAXX] + 1])
+        else:  # foreign region objects (anything with .area / .centroid / .bbox)
+            area = np.array([r.area for r in og_cell_regions], dtype=np.float64)
+            cent = np.array([r.centroid for r in og_cell_regions], dtype=np.float64).reshape(R, 2)
+            bbox = np.array([r.bbox for r in og_cell_regions], dtype=np.int64).reshape(R, 4)
+        iy, ix = cent[:, 0].astype(np.int64), cent[:, 1].astype(np.int64)  # int(centroid): truncation (:849)
+        inside = (iy >= 0) & (iy < H) & (ix >= 0) & (ix < W)               # the reference's bounds check (:850)
+        keys = np.zeros(R, dtype=np.int64)
+        if inside.any():
+            lin = (iy[inside] * W + ix[inside]).astype(np.int64)
+            keys[inside] = ops.gather(dlabels, None, torch.from_numpy(lin).to(t.device)).cpu().numpy()
+        member = np.flatnonzero(keys > 0)
+        if member.size:
+            uniq, first_at, inv = np.unique(keys[member], return_index=True, return_inverse=True)
+            order = np.argsort(first_at, kind="stable")          # groups in order of their first region (:843-878)
+            rank = np.empty_like(order)
+            rank[order] = np.arange(order.size)
+            g = rank[inv]                                        # group index of every member region
+            G = order.size
+            a_m, c_m, b_m = area[member], cent[member], bbox[member]
+            tot = np.zeros(G)
+            np.add.at(tot, g, a_m)
+            wsum = np.zeros((G, 2))
+            np.add.at(wsum, g, c_m * a_m[:, None])               # row order within a group = list order
+            lo = np.full((G, 2), np.iinfo(np.int64).max, dtype=np.int64)
+            hi = np.full((G, 2), np.iinfo(np.int64).min, dtype=np.int64)
+            np.minimum.at(lo, g, b_m[:, :2])
+            np.maximum.at(hi, g, b_m[:, 2:])
+            members_of = [[] for _ in range(G)]
+            for idx, gi in zip(member.tolist(), g.tolist()):
+                members_of[gi].append(og_cell_regions[idx])
+            centroid = wsum / tot[:, None]
+            for gi in range(G):
+                merged_regions.append({"area": tot[gi], "centroid": centroid[gi], "regions": members_of[gi],
+                                       "bbox": (int(lo[gi, 0]), int(lo[gi, 1]), int(hi[gi, 0]), int(hi[gi, 1]))})
+            processed = uniq[order].tolist()
     n = int(dcounts[0].item())
     keep = np.zeros((1, n + 1), dtype=np.uint8)
     keep[0, processed] = 1
@@ -226,6 +272,11 @@ def recreate_particle_area(ds_arr, cell_types, particle_area):
             particle_label = key
     for cell_type_label, cell_type in cell_types.items():
         if cell_type not in CELL_TYPES:
+            continue
+        if particle_label is None:
+            # no "Particle" entry: the reference's `ds_arr == None` mask is all False, its EDT then measures to the virtual
+            # point (-1, 0) and cells within DISTANCE_THRESHOLD of it would be assigned None -- a numpy error there.  Nothing
+            # can be relabelled without a particle class: leave the image as it is.
             continue
         updated_ds_arr, overlap_area = fill_particle_area(ds_arr, particle_label, cell_type_label, overlap_label=particle_label)
         particle_area += overlap_area

@@ -2,7 +2,12 @@
 
 Run in the build container only (needs ``/root/reference``):
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [--skimage auto|real|shim]
+
+``--skimage real`` insists on a real scikit-image (searched on ``sys.path`` and in ``baseline/_ref``, where the
+driver's reference install would put it) and fails without one; ``auto`` (default) uses a real one if importable
+and the restatement in ``oracle/skimage_shim`` otherwise; ``shim`` forces the restatement.  Which one produced the
+fixtures is recorded in ``reference_l2.json`` under ``_generated_with``.
 
 It imports ``/root/reference/tiff_analysis.py`` unmodified through
 ``oracle.ref_loader`` (scipy + the scikit-image shim underneath) and freezes the
@@ -31,9 +36,44 @@ def canon(summary):
     return summary
 
 
+def pick_skimage(mode):
+    """-> description of the scikit-image layer the reference will import."""
+    root = os.path.dirname(os.path.dirname(HERE))
+    ref_install = os.path.join(root, "baseline", "_ref")
+    if mode in ("auto", "real") and os.path.isdir(ref_install) and ref_install not in sys.path:
+        sys.path.insert(0, ref_install)
+    real = None
+    if mode != "shim":
+        try:
+            import skimage
+
+            if not getattr(skimage, "__version__", "").endswith("+shim"):
+                real = skimage.__version__
+        except ImportError:
+            pass
+    if mode == "real" and real is None:
+        raise SystemExit("make_golden: --skimage real, but no real scikit-image is importable (not in this image, not under baseline/_ref)")
+    if real is None:
+        for name in [m for m in sys.modules if m == "skimage" or m.startswith("skimage.")]:
+            del sys.modules[name]  # a half-imported real package must not shadow the shim
+        return "oracle/skimage_shim (restatement of scikit-image 0.25.2; the real library is not installable offline)"
+    return f"scikit-image {real} (real library)"
+
+
 def main():
-    ta = ref_loader.load_tiff_analysis()
-    arrays, meta = {}, {}
+    if os.environ.get("PYTHONHASHSEED") != "0":
+        # the reference iterates a set of cell-type names (tiff_analysis.py:794-795): with hash randomisation the member
+        # order of the "combined" groups, and with it the last bits of their area-weighted centroids, changes from run
+        # to run.  Fix the hash seed so that regenerating the fixtures reproduces them byte for byte.
+        os.execve(sys.executable, [sys.executable] + sys.argv, dict(os.environ, PYTHONHASHSEED="0"))
+    mode = "auto"
+    if "--skimage" in sys.argv:
+        mode = sys.argv[sys.argv.index("--skimage") + 1]
+    if mode not in ("auto", "real", "shim"):
+        raise SystemExit("--skimage takes auto, real or shim")
+    layer = pick_skimage(mode)
+    ta = ref_loader.load_tiff_analysis()  # installs the shim only if no real scikit-image is importable
+    arrays, meta = {}, {"_generated_with": {"skimage": layer, "reference": "tiff_analysis.py, unmodified, via oracle/ref_loader.py"}}
 
     # case A: single-channel file path (tiff_analysis.py:627-671)
     raw = synth.class_image(384, 384, seed=4321, noise=0.02)
