@@ -181,7 +181,7 @@ int pcs_min_dist_f64(const double* a, int64_t na, const double* b, int64_t nb, d
  * (refine_boundaries.py:73): every pixel joins the 4-neighbour of smallest bottleneck cost, computed by
  * tiled relaxation (pcs_watershed.cu).  Bit-identical to the sequential flood on tie-free images.
  * image float64, markers int32 (> 0 = seed; seeds outside the mask are dropped), mask_bits optional bit
- * image, labels int32 out.  BLOCKING (reads a convergence flag per sweep); max_sweeps <= 0 picks a bound
+ * image, labels int32 out.  BLOCKING (reads the convergence flags once per batch of 8 sweeps); max_sweeps <= 0 picks a bound
  * from the image size; sweeps_out (host int, optional) receives the number of sweeps. */
 size_t pcs_watershed_workspace_bytes(int B, int H, int W);
 int pcs_watershed_f64(const double* image, const int32_t* markers, const uint32_t* mask_bits, int32_t* labels, int B, int H, int W,
@@ -194,6 +194,11 @@ int pcs_gauss_f64(const double* in, double* out, double* tmp, double sigma, int 
 /* ratio = num ./ ((d0 + d1) + d2) (null denominators are skipped; all null: ratio = num);
  * *maxv = max over the non-NaN ratios (.m:45 `max(N15gauss(:)./(N15gauss(:)+N14gauss(:)))`) */
 int pcs_ratio_f64(const double* num, const double* d0, const double* d1, const double* d2, double* ratio, double* maxv, int64_t n, void* stream);
+/* one dimension of MATLAB's imresize (.m:125, :189): out[i, x] = sum_p wts[i][p] * in[idx[i][p], x], taps in order, no FMA;
+ * idx < 0 marks padding.  Strides (in elements) pick which dimension is resized; with the transposed tap table the same
+ * call applies the adjoint (per-ROI sums under resized masks: one resize per ion plane, not one per ROI). */
+int pcs_resize_taps_f64(const double* in, double* out, const int32_t* idx, const double* wts, int P, int64_t n_main, int64_t n_other,
+                        int64_t in_stride_main, int64_t in_stride_other, int64_t out_stride_main, int64_t out_stride_other, void* stream);
 /* uint8(x .* (255 / *maxv)) with MATLAB's conversion: round half away from zero, saturate, NaN -> 0 (.m:31-37) */
 int pcs_scale_u8_f64(const double* x, const double* maxv, uint8_t* out, int64_t n, void* stream);
 

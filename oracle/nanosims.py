@@ -8,8 +8,11 @@ the reference).  Decisions the restatement had to take (SURVEY.md 8a caveats):
 * ROI numbering: MATLAB ``regionprops`` on a logical numbers 8-connected
   components in COLUMN-major order of their first pixel (.m:104, :173) --
   restated as raster-order labelling of the transposed mask.
-* ``imresize`` (.m:125) is the identity when the ROI image and the acquisition
-  have the same size, which is the only case the synthetic configs use.
+* ``imresize`` (.m:125, :189) of the per-ROI ``holder`` image to the acquisition
+  size is MATLAB's default: bicubic (a = -0.5), antialiased when shrinking,
+  one dimension at a time, smaller scale first (``imresize`` below, restated from
+  the algorithm of imresize.m's ``contributions``).  With equal sizes every tap
+  table is the identity and the sums reduce to the masked sums.
 * Centroids are ``(x, y)`` = (column, row), 1-based (.m:164-165, :228-229).
 * Boundary pixels (``bwboundaries``, .m:290-291) are taken as the mask pixels with
   a 4-neighbour outside the mask; they are ``(row, col)`` 1-based and are compared
@@ -87,6 +90,67 @@ def min_dist_to_points(xy, pts):
     return np.sqrt(d2.min(axis=1))
 
 
+def _cubic(x):
+    """imresize.m ``cubic``: Keys kernel, a = -0.5."""
+    ax = np.abs(x)
+    ax2, ax3 = ax * ax, ax * ax * ax
+    return (1.5 * ax3 - 2.5 * ax2 + 1) * (ax <= 1) + (-0.5 * ax3 + 2.5 * ax2 - 4 * ax + 2) * ((1 < ax) & (ax <= 2))
+
+
+def resize_contributions(in_length, out_length, antialiasing=True):
+    """imresize.m ``contributions`` for the bicubic kernel (width 4): for every output index the 0-based source
+    indices (mirrored at the ends) and the weights (normalised to sum 1); all-zero tap columns are dropped."""
+    scale = out_length / in_length
+    kernel_width = 4.0
+    if scale < 1 and antialiasing:
+        h = lambda x: scale * _cubic(scale * x)  # noqa: E731
+        kernel_width = kernel_width / scale
+    else:
+        h = _cubic
+    x = np.arange(1, out_length + 1, dtype=np.float64)[:, None]
+    u = x / scale + 0.5 * (1 - 1 / scale)
+    left = np.floor(u - kernel_width / 2)
+    P = int(np.ceil(kernel_width)) + 2
+    indices = left + np.arange(P)[None, :]
+    weights = h(u - indices)
+    weights = weights / weights.sum(axis=1, keepdims=True)
+    aux = np.concatenate([np.arange(1, in_length + 1), np.arange(in_length, 0, -1)])
+    indices = aux[np.mod(indices.astype(np.int64) - 1, aux.size)]
+    keep = np.any(weights != 0, axis=0)
+    return (indices[:, keep] - 1).astype(np.int32), np.ascontiguousarray(weights[:, keep])
+
+
+def _apply_taps(a, idx, w, axis):
+    """out[i] = sum_p w[i, p] * a[idx[i, p]] along ``axis``, taps in order, one multiply and one add each."""
+    a = np.moveaxis(np.asarray(a, dtype=np.float64), axis, 0)
+    out = np.zeros((idx.shape[0],) + a.shape[1:])
+    for p in range(idx.shape[1]):
+        out = out + w[:, p].reshape((-1,) + (1,) * (a.ndim - 1)) * a[idx[:, p]]
+    return np.moveaxis(out, 0, axis)
+
+
+def imresize(a, out_shape, antialiasing=True):
+    """MATLAB ``imresize(A, [rows cols])`` with its defaults for a double image (.m:125): bicubic, antialiasing,
+    the dimension with the smaller scale first (rows on a tie)."""
+    a = np.asarray(a, dtype=np.float64)
+    scales = [out_shape[0] / a.shape[0], out_shape[1] / a.shape[1]]
+    for dim in sorted((0, 1), key=lambda d: scales[d]):
+        idx, w = resize_contributions(a.shape[dim], out_shape[dim], antialiasing)
+        a = _apply_taps(a, idx, w, dim)
+    return a
+
+
+def roi_sums_resized(planes, roi_labels, n_rois):
+    """.m:122-132 when the ROI image and the acquisition differ in size: per ROI, ``holder`` (1 on the ROI's pixels)
+    is resized to the acquisition size and every plane is summed under the resulting fractional mask."""
+    out = np.zeros((n_rois, planes.shape[0]))
+    for i in range(n_rois):
+        roimask = imresize((roi_labels == i + 1).astype(np.float64), planes.shape[1:])
+        for k in range(planes.shape[0]):
+            out[i, k] = (planes[k] * roimask).sum()
+    return out
+
+
 def analyse(planes, red_mask, green_mask, agg_mask, raster=19.0, acq=512.0):
     """Whole-script restatement: rows ``[set, i, sums..., act..., act*100..., x, y,
     nearest_um, boundary_um]`` for the red then the green ROIs
@@ -96,7 +160,7 @@ def analyse(planes, red_mask, green_mask, agg_mask, raster=19.0, acq=512.0):
     rows, pos = [], []
     for set_id, mask in ((1, red_mask), (2, green_mask)):
         lab, n = matlab_label(mask)
-        s = roi_sums(planes, lab, n)
+        s = roi_sums(planes, lab, n) if lab.shape == planes.shape[1:] else roi_sums_resized(planes, lab, n)
         act = activities(s, spec)
         xy = roi_centroids_xy(lab, n)
         rows.append(np.column_stack([np.full(n, float(set_id)), np.arange(1, n + 1, dtype=np.float64), s, act, act * 100.0]))

@@ -76,6 +76,7 @@ SIGNATURES = {
     "pcs_gauss_f64": (c_int, [_P, _P, _P, c_double, _I, _I, _I, _P]),
     "pcs_ratio_f64": (c_int, [_P, _P, _P, _P, _P, _P, _L, _P]),
     "pcs_scale_u8_f64": (c_int, [_P, _P, _P, _L, _P]),
+    "pcs_resize_taps_f64": (c_int, [_P, _P, _P, _P, _I, _L, _L, _L, _L, _L, _L, _P]),
     "pcs_segment_workspace_bytes": (_Z, [_I, _I, _I]),
     "pcs_segment_chunk": (c_int, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _I, _P, _Z, _P]),
     "pcs_table_finalize": (c_int, [_P, _L, _P, _I, _I, c_double, _P, _P]),

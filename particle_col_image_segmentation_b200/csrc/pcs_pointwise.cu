@@ -240,7 +240,10 @@ __global__ void k_gather(const T* __restrict__ img, const long long* __restrict_
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   long long s = slice ? slice[i] : 0;
-  out[i] = (long long)img[s * slice_elems + idx[i]];
+  const long long j = idx[i];
+  // an index outside the slice reads nothing (0 = background for every caller): a centroid of a region measured on
+  // another, larger image must not become an out-of-bounds load
+  out[i] = (j >= 0 && j < slice_elems && s >= 0) ? (long long)img[s * slice_elems + j] : 0;
 }
 
 // ---------------------------------------------------------------- C ABI

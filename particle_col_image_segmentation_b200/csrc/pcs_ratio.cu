@@ -95,6 +95,28 @@ __global__ void __launch_bounds__(256)
   out[i] = o;
 }
 
+// ---------------------------------------------------------------- imresize (.m:125, :189)
+// MATLAB resizes one dimension at a time: out[i] = sum_p w[i][p] * in[idx[i][p]] with, per output index, P taps
+// whose weights and (mirrored) source indices come from imresize's `contributions` (host side, nanosims.py).  The
+// same kernel applies the ADJOINT when it is handed the transposed tap table, which is how the per-ROI sums under
+// a resized ROI mask are computed with one resize per ion plane instead of one per ROI (nanosims.py).  Products and
+// sums are separate IEEE operations in tap order (no FMA): oracle/nanosims.py reproduces the forward resize bit for
+// bit.  Thread per output element; `main` is the resized dimension, `other` the one carried along.
+__global__ void __launch_bounds__(256)
+    k_resize_taps(const double* __restrict__ in, double* __restrict__ out, const int* __restrict__ idx, const double* __restrict__ wts,
+                  int P, long long n_main, long long n_other, long long is_main, long long is_other, long long os_main, long long os_other) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_main * n_other) return;
+  const long long i = t / n_other, x = t - i * n_other;
+  double acc = 0.0;
+  for (int p = 0; p < P; ++p) {
+    const int j = idx[i * P + p];
+    if (j < 0) continue;  // padding of a ragged (transposed) table
+    acc = __dadd_rn(acc, __dmul_rn(wts[i * P + p], in[(long long)j * is_main + x * is_other]));
+  }
+  out[i * os_main + x * os_other] = acc;
+}
+
 extern "C" {
 
 int pcs_gauss_f64(const double* in, double* out, double* tmp, double sigma, int B, int H, int W, void* stream) {
@@ -132,6 +154,15 @@ int pcs_scale_u8_f64(const double* x, const double* maxv, uint8_t* out, int64_t 
   PCS_REQUIRE(n >= 1 && x && maxv && out, "null argument");
   PCS_LAUNCH("k_scale_u8", (cudaStream_t)stream, k_scale_u8<<<pcs_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(x, maxv, out, n));
   return pcs_check_launch("scale u8");
+}
+
+int pcs_resize_taps_f64(const double* in, double* out, const int32_t* idx, const double* wts, int P, int64_t n_main, int64_t n_other,
+                        int64_t in_stride_main, int64_t in_stride_other, int64_t out_stride_main, int64_t out_stride_other, void* stream) {
+  PCS_REQUIRE(in && out && idx && wts && P >= 1 && n_main >= 1 && n_other >= 1, "bad resize arguments");
+  PCS_REQUIRE(in != out, "resize cannot run in place");
+  PCS_LAUNCH("k_resize_taps", (cudaStream_t)stream, k_resize_taps<<<pcs_blocks(n_main * n_other, 256), 256, 0, (cudaStream_t)stream>>>(
+      in, out, idx, wts, P, n_main, n_other, in_stride_main, in_stride_other, out_stride_main, out_stride_other));
+  return pcs_check_launch("resize");
 }
 
 }  // extern "C"

@@ -28,6 +28,7 @@
 #define WS_TY 16
 #define WS_INNER (2 * (WS_TX + WS_TY))
 #define WS_DINF 0x3fffffff
+#define WS_BATCH 8  // sweeps between two reads of the convergence flags
 
 struct WsState {
   double b;
@@ -60,12 +61,29 @@ __global__ void __launch_bounds__(WS_TX* WS_TY)
 __global__ void __launch_bounds__(WS_TX* WS_TY)
     k_ws_sweep(const double* __restrict__ img, const uint8_t* __restrict__ kind, const double* __restrict__ b_in,
                const int* __restrict__ d_in, const int* __restrict__ l_in, double* __restrict__ b_out, int* __restrict__ d_out,
-               int* __restrict__ l_out, int* __restrict__ changed, int H, int W) {
+               int* __restrict__ l_out, int* __restrict__ changed, const uint8_t* __restrict__ tf_in, uint8_t* __restrict__ tf_out, int H,
+               int W) {
   __shared__ double sb[2][WS_TY + 2][WS_TX + 2];
   __shared__ int sd[2][WS_TY + 2][WS_TX + 2], sl[2][WS_TY + 2][WS_TX + 2];
   const int tx = threadIdx.x % WS_TX, ty = threadIdx.x / WS_TX;
   const int x0 = blockIdx.x * WS_TX, y0 = blockIdx.y * WS_TY;
   const long long base = (long long)blockIdx.z * H * W;
+  // Active tiles only.  A tile's result depends on its own pixels and the one-pixel halo its four neighbours lend it;
+  // if none of the five changed in the previous sweep, this sweep would write what the output buffer (the input of
+  // the previous sweep) already holds.  Late sweeps touch only the tiles along the flood paths that are still
+  // growing -- on the 4096^2 touching-particle map 123 sweeps used to stream the whole state 123 times.
+  const long long tile = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  if (tf_in) {
+    int act = tf_in[tile];
+    if (blockIdx.x > 0) act |= tf_in[tile - 1];
+    if (blockIdx.x + 1 < gridDim.x) act |= tf_in[tile + 1];
+    if (blockIdx.y > 0) act |= tf_in[tile - gridDim.x];
+    if (blockIdx.y + 1 < gridDim.y) act |= tf_in[tile + gridDim.x];
+    if (!act) {
+      if (threadIdx.x == 0) tf_out[tile] = 0;
+      return;
+    }
+  }
   const double inf = __longlong_as_double(0x7ff0000000000000LL);
   // tile + one-pixel halo; outside the image (and outside the mask: b = inf there) nothing floods
   for (int i = threadIdx.x; i < (WS_TY + 2) * (WS_TX + 2); i += WS_TX * WS_TY) {
@@ -115,12 +133,18 @@ __global__ void __launch_bounds__(WS_TX* WS_TY)
     cur ^= 1;
     if (!__syncthreads_or(moved)) break;
   }
+  int diff = 0;
   if (inside) {
     const WsState last{sb[cur][ty + 1][tx + 1], sd[cur][ty + 1][tx + 1], sl[cur][ty + 1][tx + 1]};
     b_out[g] = last.b;
     d_out[g] = last.d;
     l_out[g] = last.lab;
-    if (last.b != first.b || last.d != first.d || last.lab != first.lab) *changed = 1;
+    diff = last.b != first.b || last.d != first.d || last.lab != first.lab;
+  }
+  diff = __syncthreads_or(diff);
+  if (threadIdx.x == 0) {
+    tf_out[tile] = (uint8_t)(diff != 0);
+    if (diff) *changed = 1;
   }
 }
 
@@ -128,10 +152,11 @@ extern "C" {
 
 size_t pcs_watershed_workspace_bytes(int B, int H, int W) {
   const size_t n = (size_t)B * H * W;
-  return 2 * pcs_align256(n * 8) + 4 * pcs_align256(n * 4) + pcs_align256(n) + 256;
+  const size_t tiles = (size_t)B * ((H + WS_TY - 1) / WS_TY) * ((W + WS_TX - 1) / WS_TX);
+  return 2 * pcs_align256(n * 8) + 4 * pcs_align256(n * 4) + pcs_align256(n) + 256 + 2 * pcs_align256(tiles);  // 256 B: WS_BATCH convergence flags; then two planes of per-tile "changed" flags
 }
 
-// Blocking: the sweep loop reads a convergence flag back after every sweep.  Returns PCS_OK and the number
+// Blocking: the sweep loop reads the convergence flags back once per batch of WS_BATCH sweeps.  Returns PCS_OK and the number
 // of sweeps (optional); labels receives the last state's labels (int32, 0 = not flooded).
 int pcs_watershed_f64(const double* image, const int32_t* markers, const uint32_t* mask_bits, int32_t* labels, int B, int H, int W,
                       int max_sweeps, int* sweeps_out, void* wsp, size_t ws_bytes, void* stream) {
@@ -160,6 +185,9 @@ int pcs_watershed_f64(const double* image, const int32_t* markers, const uint32_
   uint8_t* kind = (uint8_t*)p;
   p += pcs_align256(n);
   int* changed = (int*)p;
+  p += 256;
+  const size_t tiles = (size_t)B * ((H + WS_TY - 1) / WS_TY) * ((W + WS_TX - 1) / WS_TX);
+  uint8_t* tf[2] = {(uint8_t*)p, (uint8_t*)p + pcs_align256(tiles)};
   const int WW = pcs_words(W);
   PCS_LAUNCH("k_ws_init", st, k_ws_init<<<pcs_blocks((long long)n, WS_TX * WS_TY), WS_TX * WS_TY, 0, st>>>(
       image, markers, mask_bits, b[0], d[0], l[0], kind, B, H, W, WW));
@@ -168,19 +196,34 @@ int pcs_watershed_f64(const double* image, const int32_t* markers, const uint32_
     const long long bound = (long long)H * W / 16 + 4LL * (H + W) + 64;
     max_sweeps = bound > 0x7fffffffLL ? 0x7fffffff : (int)bound;
   }
-  int cur = 0, sweeps = 0, flag = 1;
-  while (flag) {
+  // Sweeps are issued in batches of WS_BATCH with one flag per sweep and ONE read-back per batch: the host no longer
+  // sits between every two sweeps.  A sweep that changes nothing leaves the state at the fixed point, so the sweeps a
+  // batch runs past convergence are no-ops and the reported count is the index of the first quiet sweep.
+  int cur = 0, sweeps = 0, launched = 0;
+  bool done = false;
+  while (!done) {
     if (sweeps >= max_sweeps) {
       pcs_set_error("watershed did not converge within max_sweeps");
       return PCS_ERR_INVALID;
     }
-    cudaMemsetAsync(changed, 0, sizeof(int), st);
-    PCS_LAUNCH("k_ws_sweep", st, k_ws_sweep<<<grid, WS_TX * WS_TY, 0, st>>>(image, kind, b[cur], d[cur], l[cur], b[cur ^ 1], d[cur ^ 1],
-                                                                              l[cur ^ 1], changed, H, W));
-    cudaMemcpyAsync(&flag, changed, sizeof(int), cudaMemcpyDeviceToHost, st);
+    int flags[WS_BATCH];
+    cudaMemsetAsync(changed, 0, sizeof(int) * WS_BATCH, st);
+    for (int i = 0; i < WS_BATCH; ++i) {
+      // the very first sweep runs every tile (and fills BOTH state buffers' worth of flags: its output flags feed sweep 2)
+      PCS_LAUNCH("k_ws_sweep", st, k_ws_sweep<<<grid, WS_TX * WS_TY, 0, st>>>(image, kind, b[cur], d[cur], l[cur], b[cur ^ 1], d[cur ^ 1],
+                                                                                l[cur ^ 1], changed + i, launched ? tf[cur] : nullptr, tf[cur ^ 1], H, W));
+      cur ^= 1;
+      ++launched;
+    }
+    cudaMemcpyAsync(flags, changed, sizeof(int) * WS_BATCH, cudaMemcpyDeviceToHost, st);
     if (cudaStreamSynchronize(st) != cudaSuccess) return pcs_check_launch("watershed sweep");
-    cur ^= 1;
-    ++sweeps;
+    for (int i = 0; i < WS_BATCH; ++i) {
+      ++sweeps;
+      if (!flags[i]) {
+        done = true;
+        break;
+      }
+    }
   }
   cudaMemcpyAsync(labels, l[cur], n * 4, cudaMemcpyDeviceToDevice, st);
   if (sweeps_out) *sweeps_out = sweeps;

@@ -36,8 +36,99 @@ def matlab_label(mask):
     return lab[0].t().contiguous(), int(counts[0].item())
 
 
+def _cubic(x):
+    ax = np.abs(x)
+    ax2, ax3 = ax * ax, ax * ax * ax
+    return (1.5 * ax3 - 2.5 * ax2 + 1) * (ax <= 1) + (-0.5 * ax3 + 2.5 * ax2 - 4 * ax + 2) * ((1 < ax) & (ax <= 2))
+
+
+def resize_contributions(in_length, out_length, antialiasing=True):
+    """Tap table of one dimension of MATLAB's ``imresize`` (bicubic, a = -0.5; the kernel is stretched by 1 / scale
+    when shrinking with antialiasing): ``(idx int32 (out, P), weights float64 (out, P))``, source indices 0-based and
+    mirrored at the ends, weights normalised per output index (imresize.m ``contributions``).  Host work: out x P
+    numbers."""
+    scale = out_length / in_length
+    kernel_width = 4.0
+    if scale < 1 and antialiasing:
+        h = lambda x: scale * _cubic(scale * x)  # noqa: E731
+        kernel_width = kernel_width / scale
+    else:
+        h = _cubic
+    x = np.arange(1, out_length + 1, dtype=np.float64)[:, None]
+    u = x / scale + 0.5 * (1 - 1 / scale)
+    left = np.floor(u - kernel_width / 2)
+    P = int(np.ceil(kernel_width)) + 2
+    indices = left + np.arange(P)[None, :]
+    weights = h(u - indices)
+    weights = weights / weights.sum(axis=1, keepdims=True)
+    aux = np.concatenate([np.arange(1, in_length + 1), np.arange(in_length, 0, -1)])
+    indices = aux[np.mod(indices.astype(np.int64) - 1, aux.size)]
+    keep = np.any(weights != 0, axis=0)
+    return (indices[:, keep] - 1).astype(np.int32), np.ascontiguousarray(weights[:, keep])
+
+
+def _transpose_taps(idx, w, in_length):
+    """The adjoint tap table: for every SOURCE index the outputs it feeds and with which weight, padded with -1."""
+    out_i, p_i = np.nonzero(w != 0)
+    src = idx[out_i, p_i]
+    order = np.lexsort((out_i, src))  # by source index, outputs ascending within it
+    src, out_i, wv = src[order], out_i[order], w[out_i, p_i][order]
+    counts = np.bincount(src, minlength=in_length)
+    Q = max(1, int(counts.max()))
+    start = np.concatenate([[0], np.cumsum(counts)[:-1]])
+    col = np.arange(src.size) - start[src]
+    tidx = np.full((in_length, Q), -1, dtype=np.int32)
+    tw = np.zeros((in_length, Q), dtype=np.float64)
+    tidx[src, col] = out_i
+    tw[src, col] = wv
+    return tidx, tw
+
+
+def _apply_taps(t, idx, w, dim):
+    """One dimension of a resize on the device: ``t`` (H, W) float64 -> the same with ``dim`` replaced by len(idx)."""
+    H, W = (int(v) for v in t.shape)
+    n_main = int(idx.shape[0])
+    out = torch.empty((n_main, W) if dim == 0 else (H, n_main), dtype=torch.float64, device=t.device)
+    d_idx = torch.from_numpy(np.ascontiguousarray(idx)).to(t.device)
+    d_w = torch.from_numpy(np.ascontiguousarray(w)).to(t.device)
+    if dim == 0:
+        args = (n_main, W, W, 1, W, 1)
+    else:
+        args = (n_main, H, 1, W, 1, n_main)
+    _lib.call("pcs_resize_taps_f64", ops._p(t), ops._p(out), ops._p(d_idx), ops._p(d_w), int(idx.shape[1]), *args, ops._stream())
+    return out
+
+
+def imresize(a, out_shape, antialiasing=True):
+    """MATLAB ``imresize(A, [rows cols])`` for a double image with the defaults the script relies on (.m:125, :189):
+    bicubic, antialiased when shrinking, one dimension at a time, the smaller scale first.  numpy in -> numpy out,
+    CUDA tensor in -> CUDA tensor out."""
+    t = _f64_image(a)
+    scales = [out_shape[0] / t.shape[0], out_shape[1] / t.shape[1]]
+    for dim in sorted((0, 1), key=lambda d: scales[d]):
+        idx, w = resize_contributions(int(t.shape[dim]), int(out_shape[dim]), antialiasing)
+        t = _apply_taps(t, idx, w, dim)
+    return _io.back(t, _io.is_numpy(a))
+
+
+def _adjoint_resize(plane, roi_shape):
+    """R^T applied to an acquisition-size plane, R = imresize from ``roi_shape`` to ``plane.shape``:
+    ``sum(plane .* imresize(holder))  ==  sum((R^T plane) .* holder)`` for every ROI's ``holder``, so the per-ROI sums
+    under resized masks (.m:125-132) cost one adjoint resize per ion plane plus the ordinary masked sums, not one
+    resize per ROI.  The dimensions are undone in the reverse of imresize's order."""
+    t = plane
+    scales = [plane.shape[0] / roi_shape[0], plane.shape[1] / roi_shape[1]]
+    for dim in reversed(sorted((0, 1), key=lambda d: scales[d])):
+        idx, w = resize_contributions(int(roi_shape[dim]), int(plane.shape[dim]))
+        tidx, tw = _transpose_taps(idx, w, int(roi_shape[dim]))
+        t = _apply_taps(t, tidx, tw, dim)
+    return t
+
+
 def _set_table(planes_d, mask, spec, set_id):
     lab, n = matlab_label(mask)
+    if tuple(lab.shape) != tuple(planes_d.shape[1:]):  # ROI image and acquisition differ in size: .m:125 resizes every ROI mask
+        planes_d = torch.stack([_adjoint_resize(planes_d[k], tuple(lab.shape)) for k in range(planes_d.shape[0])])
     sums = ops.roi_sums(lab, planes_d, n).cpu().numpy()
     tab = ops.new_table(max(1, n), lab.device)
     ops.region_table(lab.unsqueeze(0), None, tab)

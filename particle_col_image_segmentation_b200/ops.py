@@ -19,7 +19,9 @@ _DTYPE_CODE = {torch.uint8: 0, torch.uint16: 1, torch.int32: 2, torch.float32: 3
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    # the raw handle of torch's current stream; ~10x cheaper than building a torch.cuda.Stream object per launch, which
+    # mattered once the drop-in functions were down to ~60 launches of a few microseconds each
+    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
 
 
 def _p(t):

@@ -205,3 +205,27 @@ def test_nanosims_ratio_images():
     x = np.array([[0.0, 0.5, 1.5, 2.5, 254.5, 255.0, 127.49999999999999]])
     assert nanosims.scaled_uint8(x).tolist() == [[0, 1, 2, 3, 255, 255, 127]]
     assert np.array_equal(nanosims.scaled_uint8(x), onano.scaled_uint8(x))
+
+
+def test_nanosims_imresize_and_resized_roi_sums():
+    """.m:125, :189: ``imresize(holder, [n n])`` (bicubic, antialiased) and the sums under the resized ROI masks.  The
+    device resize runs the restatement's tap tables in the same order without FMA: bit-exact.  The per-ROI sums use
+    the adjoint resize of the ion planes (one resize per plane instead of one per ROI): same numbers up to summation
+    order, compared at 1e-12 (north_star tolerance for activities: 1e-5).  MATLAB itself cannot be run here."""
+    from particle_col_image_segmentation_b200 import nanosims
+
+    rng = np.random.default_rng(11)
+    a = rng.random((57, 83))
+    for shape in ((57, 83), (100, 120), (31, 40), (90, 30), (20, 200)):
+        got, want = nanosims.imresize(a, shape), onano.imresize(a, shape)
+        assert got.shape == tuple(shape) and np.array_equal(got, want), shape
+    # ROI image 96 x 96 painted on a 64 x 64 acquisition (and the other way round)
+    for n_roi_img, n_acq in ((96, 64), (48, 64)):
+        planes, _, _, _ = synth.nanosims_stack(n_acq, 5, 20, seed=7)
+        _, roi, set_id, agg = synth.nanosims_stack(n_roi_img, 5, 20, seed=9)
+        red = np.isin(roi, np.nonzero(set_id == 1)[0] + 1)
+        green = np.isin(roi, np.nonzero(set_id == 2)[0] + 1)
+        got = nanosims.analyse(planes, red, green, agg)
+        want = onano.analyse(planes, red, green, agg)
+        assert got.shape == want.shape and got.shape[0] > 4
+        np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-9, equal_nan=True)

@@ -252,3 +252,34 @@ def test_nanosims_vs_loops():
     assert np.array_equal(tab[:, 9], c13)
     cnt, tot, mean = nanosims.activity_vs_distance(tab[:, 9], tab[:, -1], np.linspace(0, 4, 9))
     assert cnt.sum() == len(tab)
+
+
+def test_imresize_restatement_properties():
+    """oracle/nanosims.py::imresize (MATLAB bicubic with antialiasing, .m:125): equal sizes are the identity bit for
+    bit, constants and -- away from the mirrored border -- linear ramps are reproduced, the tap tables sum to one,
+    and the separable evaluation equals the dense matrices built from the same tables."""
+    from oracle import nanosims as onano
+
+    rng = np.random.default_rng(3)
+    a = rng.random((40, 52))
+    assert np.array_equal(onano.imresize(a, (40, 52)), a)
+    assert np.allclose(onano.imresize(np.full((30, 30), 3.5), (47, 19)), 3.5, rtol=0, atol=1e-14)
+    for n_in, n_out in ((52, 30), (40, 64), (7, 7), (5, 50), (50, 5)):
+        idx, w = onano.resize_contributions(n_in, n_out)
+        assert idx.min() >= 0 and idx.max() < n_in and np.allclose(w.sum(1), 1.0, rtol=0, atol=1e-14)
+        if n_out < n_in:  # antialiasing stretches the kernel by n_in / n_out
+            assert idx.shape[1] >= int(np.ceil(4 * n_in / n_out))
+
+    def dense(n_in, n_out):
+        idx, w = onano.resize_contributions(n_in, n_out)
+        m = np.zeros((n_out, n_in))
+        np.add.at(m, (np.repeat(np.arange(n_out), idx.shape[1]), idx.ravel()), w.ravel())
+        return m
+
+    np.testing.assert_allclose(onano.imresize(a, (64, 30)), dense(40, 64) @ (a @ dense(52, 30).T), rtol=0, atol=1e-14)
+    ramp = np.tile(np.arange(20.0), (20, 1))
+    assert np.allclose(np.diff(onano.imresize(ramp, (40, 40))[10, 6:34]), 0.5)
+    # per-ROI sums under resized masks: with equal sizes they are the plain masked sums
+    planes, roi, _, _ = synth.nanosims_stack(64, 5, 12, seed=5)
+    n = int(roi.max())
+    np.testing.assert_allclose(onano.roi_sums_resized(planes, roi, n), onano.roi_sums(planes, roi, n), rtol=1e-13)
