@@ -68,6 +68,9 @@ int pcs_gather(const void* img, int dtype, const int64_t* slice, const int64_t* 
 /* dst[i] = value for n_words uint32 (multiple of 4, dst 16-byte aligned): grid-stride 128-bit stores; doubles as
  * the store-only bandwidth probe of bench.py */
 int pcs_fill_u32(void* dst, uint32_t value, size_t n_words, void* stream);
+/* zero `bytes` (multiple of 32, 32-byte aligned) with a small persistent grid (ctas_per_sm CTAs of 128 threads per SM):
+ * for a side stream, beside kernels that leave DRAM idle */
+int pcs_zero_background(void* dst, size_t bytes, int ctas_per_sm, void* stream);
 
 /* ---- K1: histogram + Otsu ------------------------------------------------------
  * skimage.filters.threshold_otsu on uint16 slices (north_star).

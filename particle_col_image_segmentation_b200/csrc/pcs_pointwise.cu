@@ -388,6 +388,28 @@ int pcs_gather(const void* img, int dtype, const int64_t* slice, const int64_t* 
   return pcs_check_launch("gather");
 }
 
+// Background fill: a SMALL persistent grid (ctas_per_sm CTAs of 128 threads per SM, 256-bit stores) meant to run on a side
+// stream beside kernels that leave DRAM idle.  Every CTA is resident from the start, so the block scheduler keeps
+// dispatching the other streams' kernels into the rest of each SM (a grid with pending CTAs keeps them out).
+__global__ void __launch_bounds__(128) k_fill_background(uint4* __restrict__ p, size_t n16) {
+  size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 2;
+  const size_t stride = (size_t)gridDim.x * blockDim.x * 2;
+  for (; i + 1 < n16; i += stride)
+    asm volatile("st.global.v8.u32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"l"(p + i), "r"(0u) : "memory");
+  if (i < n16) p[i] = make_uint4(0, 0, 0, 0);
+}
+
+int pcs_zero_background(void* dst, size_t bytes, int ctas_per_sm, void* stream) {
+  PCS_REQUIRE(dst != nullptr && (bytes & 31) == 0 && ((((uintptr_t)dst) & 31) == 0), "background fill needs a 32-byte aligned buffer of 32k bytes");
+  if (bytes == 0) return PCS_OK;
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  PCS_LAUNCH("k_fill_background", (cudaStream_t)stream, k_fill_background<<<sms * ctas_per_sm, 128, 0, (cudaStream_t)stream>>>((uint4*)dst, bytes / 16));
+  return pcs_check_launch("background fill");
+}
+
 int pcs_fill_u32(void* dst, uint32_t value, size_t n_words, void* stream) {
   PCS_REQUIRE(dst != nullptr && (n_words & 3) == 0 && ((((uintptr_t)dst) & 15) == 0), "fill needs a 16-byte aligned buffer of 4k words");
   if (n_words == 0) return PCS_OK;
