@@ -802,6 +802,7 @@ struct PcsRefineSparse {
   int* hpar;          // parent planes of the hole forest
   int* clist;         // per slice: candidate words
   int* ccount;        // per slice: how many
+  uint8_t* mask;      // uint8 copy of the kept words (the refined mask before the holes are added), optional
 };
 
 template <bool PLANES>
@@ -902,6 +903,7 @@ __global__ void __launch_bounds__(REFINE_MAX_WARPS * 32)
       if (k < WW) {
         kw[k] = kept;
         kept_out[row * (long long)WW + k] = kept;
+        if (PLANES && sp.mask) pcs_store_mask_bytes(sp.mask + row * (long long)W, k, W, kept);  // holes are patched in by k_hole_apply_list
       }
     }
   }
@@ -1068,31 +1070,35 @@ __global__ void __launch_bounds__(HOLE_LIST_THREADS)
   }
 }
 
-// thread per word: refined = kept | candidate runs whose root is unmarked (closed: a hole); bits + optional uint8 copy
-__global__ void __launch_bounds__(PCS_CCL_THREADS)
-    k_hole_select(const uint32_t* __restrict__ kept, const uint32_t* __restrict__ cand, const int* __restrict__ hpar,
-                  uint32_t* __restrict__ out, uint8_t* __restrict__ mask, int H, int W, int WW) {
-  const int NW = H * WW;
-  const int gw = blockIdx.x * blockDim.x + threadIdx.x;
-  if (gw >= NW) return;
+// thread per listed candidate word: the candidate runs whose root is unmarked are closed -- holes -- and are added to
+// the refined word and its uint8 copy (which k_refine_rows wrote without them)
+__global__ void __launch_bounds__(HOLE_LIST_THREADS)
+    k_hole_apply_list(const uint32_t* __restrict__ cand, const int* __restrict__ hpar, const int* __restrict__ clist,
+                      const int* __restrict__ ccount, uint32_t* __restrict__ out, uint8_t* __restrict__ mask, int H, int W, int WW) {
   const long long b = blockIdx.y;
-  const long long t = b * NW + gw;
-  uint32_t o = __ldg(kept + t);
-  const uint32_t C = __ldg(cand + t);
-  if (C) {
-    const int* par = hpar + b * ((long long)NW << 4);
+  const int NW = H * WW;
+  const int n = min(ccount[b], NW);
+  const int* par = hpar + b * ((long long)NW << 4);
+  const int* cl = clist + b * (long long)NW;
+  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < n; it += gridDim.x * blockDim.x) {
+    const int gw = cl[it];
+    const long long t = b * NW + gw;
+    const uint32_t C = __ldg(cand + t);
+    uint32_t add = 0;
     uint32_t S = C & ~(C << 1);
     for (int j = 0; S; ++j) {
       int s;
       const uint32_t R = pcs_pop_run(C, S, s);
       const int r = pcs_hole_root(par, NW, pcs_node<4>(gw, j));
-      if (pcs_ld_cg(par + pcs_slot<4>(r, NW)) >= 0) o |= R;
+      if (pcs_ld_cg(par + pcs_slot<4>(r, NW)) >= 0) add |= R;
     }
-  }
-  out[t] = o;
-  if (mask) {
-    const int y = gw / WW, k = gw - y * WW;
-    pcs_store_mask_bytes(mask + (b * H + y) * (long long)W, k, W, o);
+    if (!add) continue;
+    const uint32_t o = out[t] | add;
+    out[t] = o;
+    if (mask) {
+      const int y = gw / WW, k = gw - y * WW;
+      pcs_store_mask_bytes(mask + (b * H + y) * (long long)W, k, W, o);
+    }
   }
 }
 
@@ -1196,11 +1202,11 @@ int pcs_ccl_scan_offsets(const PcsCclWs& ws, int32_t* counts, int B, int H, int 
 }
 
 // The refine stage of the pipeline (remove_small_objects + binary_fill_holes, tiff_analysis.py:769-773, :880) on the
-// labelled mask: run labels from the parent planes, hole candidates resolved over their list.  kept / cand: bit
-// planes of scratch; hpar: parent planes of scratch (B * 16 * NW ints); clist / ccount: B * NW / B ints.
+// labelled mask: run labels from the parent planes, hole candidates resolved over their list.  cand: bit
+// plane of scratch; hpar: parent planes of scratch (B * 16 * NW ints); clist / ccount: B * NW / B ints.
 int pcs_seg_refine_stage(const uint32_t* bits, const int* labpar, const int64_t* table, int64_t cap, const int32_t* offsets,
-                         int64_t min_size, uint32_t* out, uint8_t* out_mask, uint32_t* kept, uint32_t* cand, int* hpar, int* clist,
-                         int* ccount, int B, int H, int W, cudaStream_t st) {
+                         int64_t min_size, uint32_t* out, uint8_t* out_mask, uint32_t* cand, int* hpar, int* clist, int* ccount, int B,
+                         int H, int W, cudaStream_t st) {
   const int WW = pcs_words(W);
   const long long NW = (long long)H * WW, rows = (long long)B * H;
   const size_t warp_bytes = refine_words_per_warp(WW) * 4;
@@ -1210,17 +1216,19 @@ int pcs_seg_refine_stage(const uint32_t* bits, const int* labpar, const int64_t*
   static bool attr_set[64] = {};
   if (pcs_first_use(attr_set)) cudaFuncSetAttribute(k_refine_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, REFINE_SMEM_LIMIT);
   cudaMemsetAsync(ccount, 0, (size_t)B * 4, st);
+  // the kept words go straight to the refined bit plane and its uint8 copy; the hole stage reads that plane as "kept" and
+  // patches the few words that gain hole pixels
   PCS_LAUNCH("k_refine_rows", st, (k_refine_rows<true><<<pcs_blocks(rows, warps), warps * 32, warps * warp_bytes, st>>>(
-      bits, nullptr, (const long long*)table, cap, offsets, min_size > 1 ? min_size : 1, kept, cand, rows, H, W, WW,
-      PcsRefineSparse{labpar, hpar, clist, ccount})));
+      bits, nullptr, (const long long*)table, cap, offsets, min_size > 1 ? min_size : 1, out, cand, rows, H, W, WW,
+      PcsRefineSparse{labpar, hpar, clist, ccount, out_mask})));
   // candidates are rare: a few CTAs per slice cover the usual list, the grid-stride loop the unusual one
   long long gx = (NW / 64 + HOLE_LIST_THREADS - 1) / HOLE_LIST_THREADS;
   if (gx < 1) gx = 1;
   if (gx > 256) gx = 256;
   dim3 gl((unsigned)gx, B);
   PCS_LAUNCH("k_hole_union_list", st, (k_hole_union_list<<<gl, HOLE_LIST_THREADS, 0, st>>>(cand, hpar, clist, ccount, H, WW)));
-  PCS_LAUNCH("k_hole_mark_list", st, (k_hole_mark_list<<<gl, HOLE_LIST_THREADS, 0, st>>>(kept, cand, hpar, clist, ccount, H, W, WW)));
-  PCS_LAUNCH("k_hole_select", st, (k_hole_select<<<dim3(pcs_blocks(NW, PCS_CCL_THREADS), B), PCS_CCL_THREADS, 0, st>>>(kept, cand, hpar, out, out_mask, H, W, WW)));
+  PCS_LAUNCH("k_hole_mark_list", st, (k_hole_mark_list<<<gl, HOLE_LIST_THREADS, 0, st>>>(out, cand, hpar, clist, ccount, H, W, WW)));
+  PCS_LAUNCH("k_hole_apply_list", st, (k_hole_apply_list<<<gl, HOLE_LIST_THREADS, 0, st>>>(cand, hpar, clist, ccount, out, out_mask, H, W, WW)));
   return pcs_check_launch("segment: refine stage");
 }
 

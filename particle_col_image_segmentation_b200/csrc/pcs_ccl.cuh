@@ -181,5 +181,5 @@ int pcs_seg_label_stage(const uint16_t* img, const int32_t* thr, int median, uin
                         int32_t* counts, int64_t* table, int64_t cap, const PcsCclWs& ws, int* rsum, int* wlist, int* wcount, int B, int H,
                         int W, cudaStream_t st);
 int pcs_seg_refine_stage(const uint32_t* bits, const int* labpar, const int64_t* table, int64_t cap, const int32_t* offsets,
-                         int64_t min_size, uint32_t* out, uint8_t* out_mask, uint32_t* kept, uint32_t* cand, int* hpar, int* clist,
-                         int* ccount, int B, int H, int W, cudaStream_t st);
+                         int64_t min_size, uint32_t* out, uint8_t* out_mask, uint32_t* cand, int* hpar, int* clist, int* ccount, int B,
+                         int H, int W, cudaStream_t st);

@@ -99,7 +99,7 @@ int pcs_segment_chunk(const uint16_t* img, int B, int H, int W, int denoise_size
     // word list of the labelling stage are free by now and serve as the hole forest and the candidate list
     PcsCclWs cw;
     STEP(pcs_ccl_ws_carve(w.ccl, w.ccl_bytes, B, H, W, 0, &cw));
-    STEP(pcs_seg_refine_stage(bits, cw.parent, table, cap, offsets, min_size, w.refined, refined, w.keep, w.raw, w.rsum, w.wlist, w.wcount, B, H, W, (cudaStream_t)stream));
+    STEP(pcs_seg_refine_stage(bits, cw.parent, table, cap, offsets, min_size, w.refined, refined, w.raw, w.rsum, w.wlist, w.wcount, B, H, W, (cudaStream_t)stream));
   } else {
     STEP(pcs_refine_labeled_bits(bits, labels, table, cap, offsets, min_size > 1 ? min_size : 1, w.refined, refined, B, H, W, w.ccl, w.ccl_bytes, stream));
   }
