@@ -992,16 +992,9 @@ __global__ void __launch_bounds__(REFINE_MAX_WARPS * 32)
 #define HOLE_LIST_THREADS 128
 
 // 4-connected unions between candidate runs: with the word to the left and with the row above
-__global__ void __launch_bounds__(HOLE_LIST_THREADS)
-    k_hole_union_list(const uint32_t* __restrict__ cand, int* __restrict__ hpar, const int* __restrict__ clist,
-                      const int* __restrict__ ccount, int H, int WW) {
-  const long long b = blockIdx.y;
-  const int NW = H * WW;
-  const int n = min(ccount[b], NW);
-  const uint32_t* cc = cand + b * (long long)NW;
-  int* par = hpar + b * ((long long)NW << 4);
-  const int* cl = clist + b * (long long)NW;
-  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < n; it += gridDim.x * blockDim.x) {
+__device__ __forceinline__ void hole_union_pass(const uint32_t* __restrict__ cc, int* __restrict__ par, const int* __restrict__ cl, int n,
+                                                int NW, int WW, int first, int stride) {
+  for (int it = first; it < n; it += stride) {
     const int gw = cl[it], y = gw / WW, k = gw - y * WW;
     const uint32_t C = __ldg(cc + gw);
     if (k > 0 && (C & 1u)) {
@@ -1036,20 +1029,12 @@ __device__ __forceinline__ int pcs_hole_root(const int* par, int NW, int n) {  /
 }
 
 // candidate runs that touch the image border or background outside the candidate set are open: mark their roots
-__global__ void __launch_bounds__(HOLE_LIST_THREADS)
-    k_hole_mark_list(const uint32_t* __restrict__ kept, const uint32_t* __restrict__ cand, int* __restrict__ hpar,
-                     const int* __restrict__ clist, const int* __restrict__ ccount, int H, int W, int WW) {
-  const long long b = blockIdx.y;
-  const int NW = H * WW;
-  const int n = min(ccount[b], NW);
-  const uint32_t* kk = kept + b * (long long)NW;
-  const uint32_t* cc = cand + b * (long long)NW;
-  int* par = hpar + b * ((long long)NW << 4);
-  const int* cl = clist + b * (long long)NW;
-  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < n; it += gridDim.x * blockDim.x) {
+__device__ __forceinline__ void hole_mark_pass(const uint32_t* __restrict__ kk, const uint32_t* __restrict__ cc, int* __restrict__ par,
+                                               const int* __restrict__ cl, int n, int NW, int H, int W, int WW, int first, int stride) {
+  for (int it = first; it < n; it += stride) {
     const int gw = cl[it], y = gw / WW, k = gw - y * WW;
     const uint32_t C = __ldg(cc + gw);
-    auto open_at = [&](int w, int kw) { return ~__ldg(kk + w) & ~__ldg(cc + w) & pcs_valid_mask(kw, W); };
+    auto open_at = [&](int w, int kw) { return ~kk[w] & ~__ldg(cc + w) & pcs_valid_mask(kw, W); };  // kk is the refined plane this kernel patches later: plain loads
     const uint32_t n_c = open_at(gw, k);
     uint32_t adj = (n_c << 1) | (n_c >> 1);
     adj |= (k > 0) ? (open_at(gw - 1, k - 1) >> 31) : 1u;
@@ -1072,18 +1057,13 @@ __global__ void __launch_bounds__(HOLE_LIST_THREADS)
 
 // thread per listed candidate word: the candidate runs whose root is unmarked are closed -- holes -- and are added to
 // the refined word and its uint8 copy (which k_refine_rows wrote without them)
-__global__ void __launch_bounds__(HOLE_LIST_THREADS)
-    k_hole_apply_list(const uint32_t* __restrict__ cand, const int* __restrict__ hpar, const int* __restrict__ clist,
-                      const int* __restrict__ ccount, uint32_t* __restrict__ out, uint8_t* __restrict__ mask, int H, int W, int WW) {
-  const long long b = blockIdx.y;
-  const int NW = H * WW;
-  const int n = min(ccount[b], NW);
-  const int* par = hpar + b * ((long long)NW << 4);
-  const int* cl = clist + b * (long long)NW;
-  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < n; it += gridDim.x * blockDim.x) {
+__device__ __forceinline__ void hole_apply_pass(const uint32_t* __restrict__ cand, const int* __restrict__ par, const int* __restrict__ cl,
+                                                int n, long long b, uint32_t* __restrict__ out, uint8_t* __restrict__ mask, int NW, int H, int W,
+                                                int WW, int first, int stride) {
+  for (int it = first; it < n; it += stride) {
     const int gw = cl[it];
     const long long t = b * NW + gw;
-    const uint32_t C = __ldg(cand + t);
+    const uint32_t C = cand[t];
     uint32_t add = 0;
     uint32_t S = C & ~(C << 1);
     for (int j = 0; S; ++j) {
@@ -1100,6 +1080,28 @@ __global__ void __launch_bounds__(HOLE_LIST_THREADS)
       pcs_store_mask_bytes(mask + (b * H + y) * (long long)W, k, W, o);
     }
   }
+}
+
+// CTA per slice: the three passes of the hole stage -- unions between candidate runs, marking of the components that
+// touch open background, patching of the closed ones into the refined words -- with block barriers in between.
+// Slices are independent problems, so one CTA per slice needs no grid-wide synchronisation, and with the usual handful
+// of candidates per slice the three passes cost one launch instead of three (each was launch latency only).  A slice
+// with very many candidates just takes more trips through the block-stride loops.
+__global__ void __launch_bounds__(1024)
+    k_hole_resolve_list(const uint32_t* __restrict__ cand, int* __restrict__ hpar, const int* __restrict__ clist,
+                        const int* __restrict__ ccount, uint32_t* __restrict__ out, uint8_t* __restrict__ mask, int H, int W, int WW) {
+  const long long b = blockIdx.x;
+  const int NW = H * WW;
+  const int n = min(ccount[b], NW);
+  if (n == 0) return;
+  const uint32_t* cc = cand + b * (long long)NW;
+  int* par = hpar + b * ((long long)NW << 4);
+  const int* cl = clist + b * (long long)NW;
+  hole_union_pass(cc, par, cl, n, NW, WW, threadIdx.x, blockDim.x);
+  __syncthreads();
+  hole_mark_pass(out + b * (long long)NW, cc, par, cl, n, NW, H, W, WW, threadIdx.x, blockDim.x);
+  __syncthreads();
+  hole_apply_pass(cand, par, cl, n, b, out, mask, NW, H, W, WW, threadIdx.x, blockDim.x);
 }
 
 // thread per group of 4 words: seeds = candidate pixels on the top / bottom image row or 4-adjacent to
@@ -1221,14 +1223,7 @@ int pcs_seg_refine_stage(const uint32_t* bits, const int* labpar, const int64_t*
   PCS_LAUNCH("k_refine_rows", st, (k_refine_rows<true><<<pcs_blocks(rows, warps), warps * 32, warps * warp_bytes, st>>>(
       bits, nullptr, (const long long*)table, cap, offsets, min_size > 1 ? min_size : 1, out, cand, rows, H, W, WW,
       PcsRefineSparse{labpar, hpar, clist, ccount, out_mask})));
-  // candidates are rare: a few CTAs per slice cover the usual list, the grid-stride loop the unusual one
-  long long gx = (NW / 64 + HOLE_LIST_THREADS - 1) / HOLE_LIST_THREADS;
-  if (gx < 1) gx = 1;
-  if (gx > 256) gx = 256;
-  dim3 gl((unsigned)gx, B);
-  PCS_LAUNCH("k_hole_union_list", st, (k_hole_union_list<<<gl, HOLE_LIST_THREADS, 0, st>>>(cand, hpar, clist, ccount, H, WW)));
-  PCS_LAUNCH("k_hole_mark_list", st, (k_hole_mark_list<<<gl, HOLE_LIST_THREADS, 0, st>>>(out, cand, hpar, clist, ccount, H, W, WW)));
-  PCS_LAUNCH("k_hole_apply_list", st, (k_hole_apply_list<<<gl, HOLE_LIST_THREADS, 0, st>>>(cand, hpar, clist, ccount, out, out_mask, H, W, WW)));
+  PCS_LAUNCH("k_hole_resolve_list", st, (k_hole_resolve_list<<<B, 1024, 0, st>>>(cand, hpar, clist, ccount, out, out_mask, H, W, WW)));
   return pcs_check_launch("segment: refine stage");
 }
 
