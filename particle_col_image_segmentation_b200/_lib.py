@@ -99,11 +99,19 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    default_lib = "PCS_LIB_PATH" not in os.environ
+    stale = False
+    if default_lib:
+        from . import build as _build
+
+        stale = _build.needs_build()  # missing, or built from other sources than the ones in the tree (content hash)
+    if not os.path.exists(LIB_PATH) or stale:
         try:
             _build_if_possible()
         except Exception as e:  # noqa: BLE001
-            raise PcsError(f"libpcs.so is missing and could not be built: {e}") from e
+            raise PcsError(f"libpcs.so is {'stale' if os.path.exists(LIB_PATH) else 'missing'} and could not be built: {e}") from e
+        if default_lib and _build.needs_build():
+            raise PcsError("libpcs.so does not match the sources in csrc/ and no nvcc is at hand to rebuild it; run `python __graft_entry__.py` where nvcc is. A stale library is never used.")
     if not os.path.exists(LIB_PATH):
         raise PcsError(f"libpcs.so not found at {LIB_PATH}; run `python __graft_entry__.py` (build()) first. There is no CPU fallback.")
     lib = ctypes.CDLL(LIB_PATH)

@@ -21,12 +21,35 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
+def _deps():
+    return sorted(sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.inc")) + [os.path.join(HERE, "..", "include", "pcs.h")])
+
+
+def source_hash():
+    """Hash of every file the library is built from.  Stored next to the library by ``build()`` and compared by
+    ``_lib.load()``: a library older than its sources is rebuilt (or refused), never silently used.  Content, not
+    mtimes: a snapshot copied to another box keeps the former and not necessarily the latter."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for d in _deps():
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(f for f in FLAGS if not os.path.isabs(f) and not f.startswith(HERE)).encode())  # flags, not paths: the tree moves between boxes
+    return h.hexdigest()
+
+
+def built_hash():
+    try:
+        with open(LIB + ".hash") as f:
+            return f.read().strip()
+    except OSError:
+        return None
+
+
 def needs_build():
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.inc")) + [os.path.join(HERE, "..", "include", "pcs.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return not os.path.exists(LIB) or built_hash() != source_hash()
 
 
 def build(force=False, verbose=False, variant=None, extra_flags=()):
@@ -55,6 +78,9 @@ def build(force=False, verbose=False, variant=None, extra_flags=()):
     if failed:
         raise RuntimeError("nvcc failed building libpcs.so")
     subprocess.check_call([NVCC, "-shared", "-o", lib, *objs, "-lcudart"])
+    if not variant:
+        with open(LIB + ".hash", "w") as f:
+            f.write(source_hash() + "\n")
     return lib
 
 
