@@ -449,7 +449,24 @@ def run_b200(args):
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         d2h = sum(v.numel() * v.element_size() for k, v in host_out.items() if k != "table") + nrows * 13 * 8
-        e2e = {"value": voxels / float(tt.item()) / 1e6, "unit": "Mvoxel/s", "h2d_bytes_per_step": host_in.numel() * 2, "d2h_bytes_per_step": int(d2h), "ms_per_step": float(tt.item()) * 1e3, "chunk": args.e2e_chunk, "overlap": "H2D, kernels and D2H of consecutive chunks on three streams", "cpus_bound_near_gpu": numa}
+        e2e = {"value": voxels / float(tt.item()) / 1e6, "unit": "Mvoxel/s", "h2d_bytes_per_step": host_in.numel() * 2, "d2h_bytes_per_step": int(d2h), "ms_per_step": float(tt.item()) * 1e3, "chunk": args.e2e_chunk, "overlap": "H2D, kernels and D2H of consecutive chunks on three streams", "cpus_bound_near_gpu": numa,
+               "outputs": "mask, labels, refined, edt + table (everything the pipeline produces: 14 B/voxel back over PCIe, 8 of them the float64 EDT)"}
+        # the same call for a caller that needs the region table and the label image only: 4 B/voxel back
+        sel = ("labels",)
+        host_sel = {k: host_out[k] for k in sel + ("threshold", "counts")}
+        split_zstack.segment_zstack_pinned(host_in, host_sel, chunk=args.e2e_chunk, outputs=sel)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            nrows = split_zstack.segment_zstack_pinned(host_in, host_sel, chunk=args.e2e_chunk, outputs=sel)
+        barrier()
+        ts = torch.tensor([(time.perf_counter() - t0) / args.e2e_steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        e2e["table_and_labels"] = {"value": voxels / float(ts.item()) / 1e6, "unit": "Mvoxel/s", "ms_per_step": float(ts.item()) * 1e3, "h2d_bytes_per_step": host_in.numel() * 2,
+                                   "d2h_bytes_per_step": int(host_sel["labels"].numel() * 4 + 2 * Z * 4 + nrows * 13 * 8)}
+        if world > 1:
+            e2e["note"] = f"{world} ranks share the host: the aggregate pinned traffic ({world} x {int(d2h + host_in.numel() * 2) >> 20} MiB per step) is bounded by the host's memory / PCIe root complexes, not by the GPUs"
 
     if rank != 0:
         if world > 1:

@@ -88,7 +88,7 @@ def process_tif(input_file, channel_indices=(1, 2), move=True):
     return written
 
 
-def segment_tif(path, channel=1, **kwargs):
+def segment_tif(path, channel=1, outputs=("mask", "labels", "refined", "edt"), **kwargs):
     """Read a ``(Z, C, Y, X)`` (or ``(Z, Y, X)``) uint16 stack file into pinned memory and run the segment
     pipeline on one channel; returns the dict of pinned host tensors of ``segment_zstack_pinned``."""
     from . import tiff_io
@@ -100,8 +100,8 @@ def segment_tif(path, channel=1, **kwargs):
             t = t.pin_memory()
     if t.dim() != 3 or t.dtype != torch.uint16:
         raise _lib.PcsError(f"segment_tif expects a uint16 (Z, [C,] Y, X) stack, got {tuple(t.shape)} {t.dtype}")
-    out = alloc_host_outputs(*t.shape)
-    segment_zstack_pinned(t, out, **kwargs)
+    out = alloc_host_outputs(*t.shape, outputs=outputs)
+    segment_zstack_pinned(t, out, outputs=outputs, **kwargs)
     return out
 
 
@@ -281,24 +281,34 @@ def segment_zstack(stack, denoise_size=5, min_size=20, chunk=16, max_regions_per
 _E2E_CACHE = {}
 
 
-def alloc_host_outputs(Z, H, W):
-    """Pinned host buffers for every pipeline output of a ``(Z, H, W)`` stack."""
-    return {
-        "mask": torch.empty((Z, H, W), dtype=torch.uint8).pin_memory(),
-        "labels": torch.empty((Z, H, W), dtype=torch.int32).pin_memory(),
-        "refined": torch.empty((Z, H, W), dtype=torch.uint8).pin_memory(),
-        "edt": torch.empty((Z, H, W), dtype=torch.float64).pin_memory(),
-        "threshold": torch.empty(Z, dtype=torch.int32).pin_memory(),
-        "counts": torch.empty(Z, dtype=torch.int32).pin_memory(),
-    }
+IMAGE_OUTPUTS = {"mask": torch.uint8, "labels": torch.int32, "refined": torch.uint8, "edt": torch.float64}
 
 
-def segment_zstack_pinned(host_in, host_out, denoise_size=5, min_size=20, chunk=16, max_regions_per_slice=1 << 14):
+def alloc_host_outputs(Z, H, W, outputs=("mask", "labels", "refined", "edt")):
+    """Pinned host buffers for the chosen image outputs of a ``(Z, H, W)`` stack (plus the per-slice threshold and
+    region count, which always come back, like the region table).  What is not listed never crosses PCIe: the
+    float64 EDT alone is 8 of the 14 output bytes per voxel."""
+    for k in outputs:
+        if k not in IMAGE_OUTPUTS:
+            raise ValueError(f"unknown output {k!r}; choose from {sorted(IMAGE_OUTPUTS)}")
+    out = {k: torch.empty((Z, H, W), dtype=IMAGE_OUTPUTS[k]).pin_memory() for k in outputs}
+    out["threshold"] = torch.empty(Z, dtype=torch.int32).pin_memory()
+    out["counts"] = torch.empty(Z, dtype=torch.int32).pin_memory()
+    return out
+
+
+def segment_zstack_pinned(host_in, host_out, denoise_size=5, min_size=20, chunk=16, max_regions_per_slice=1 << 14, outputs=None):
     """Host buffers in, host buffers out.  The stack moves through the device chunk by chunk on three
     streams -- H2D copy of chunk i+1, the pipeline on chunk i and the D2H copy of the outputs of chunk
-    i-1 overlap, so the call costs about as much as its largest leg (the 14 B/voxel of outputs over
-    PCIe).  Device buffers are cached between calls.  Returns the number of table rows
-    (``host_out['table']`` holds them)."""
+    i-1 overlap, so the call costs about as much as its largest leg (with every output: the 14 B/voxel
+    coming back over PCIe).  ``outputs`` picks the image outputs that are copied back (default: the
+    ones ``host_out`` has buffers for); the table, thresholds and counts always are.  Device buffers
+    are cached between calls.  Returns the number of table rows (``host_out['table']`` holds them)."""
+    if outputs is None:
+        outputs = tuple(k for k in ("edt", "labels", "mask", "refined") if k in host_out)
+    for k in outputs:
+        if k not in IMAGE_OUTPUTS or k not in host_out:
+            raise ValueError(f"output {k!r} is unknown or has no buffer in host_out")
     dev = _io.device()
     key = (str(dev), tuple(host_in.shape), denoise_size, min_size, chunk, max_regions_per_slice)
     st = _E2E_CACHE.get(key)
@@ -326,7 +336,7 @@ def segment_zstack_pinned(host_in, host_out, denoise_size=5, min_size=20, chunk=
         st["ev_out"][i].record(main)
         with torch.cuda.stream(st["d2h"]):
             st["d2h"].wait_event(st["ev_out"][i])
-            for k in ("edt", "labels", "mask", "refined"):
+            for k in outputs:
                 host_out[k][a:b].copy_(getattr(res, k)[a:b], non_blocking=True)
     main.wait_stream(st["d2h"])
     for k in ("threshold", "counts"):

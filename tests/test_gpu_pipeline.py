@@ -99,6 +99,14 @@ def test_pinned_host_path(seg):
     assert n == len(want["table"]) and np.array_equal(host_out["table"].numpy(), want["table"])
     assert np.array_equal(host_out["labels"].numpy(), want["labels"]) and np.array_equal(host_out["edt"].numpy(), want["edt"])
     assert np.array_equal(host_out["mask"].numpy().astype(bool), want["mask"]) and np.array_equal(host_out["refined"].numpy().astype(bool), want["refined"])
+    # a caller that only needs the table and the labels: nothing else crosses PCIe, the answers are the same
+    sel = seg.alloc_host_outputs(*stack.shape, outputs=("labels",))
+    assert set(sel) == {"labels", "threshold", "counts"}
+    n2 = seg.segment_zstack_pinned(host_in, sel, chunk=2, outputs=("labels",))
+    assert n2 == n and np.array_equal(sel["table"].numpy(), want["table"]) and np.array_equal(sel["labels"].numpy(), want["labels"])
+    assert np.array_equal(sel["threshold"].numpy(), want["threshold"])
+    with pytest.raises(ValueError):
+        seg.segment_zstack_pinned(host_in, sel, outputs=("edt",))  # no buffer for it
 
 
 def test_fill_holes_from_table_matches_scipy(seg):
