@@ -68,6 +68,36 @@ __device__ __forceinline__ void seg_lunion(int* sp, int a, int b) {
   }
 }
 
+// ---------------------------------------------------------------- TMA (bulk async copy) + mbarrier helpers
+// cp.async.bulk (1-D): the copy engine of the SM moves a contiguous run of bytes from global to shared memory and
+// signals an mbarrier with the byte count; no thread holds the data in registers on the way (SASS: UBLKCP).
+// Measured on B200 (2048^2 x 64, profiles/README.md): 335 us per step with the bulk copies against 297 us with plain
+// 128-bit loads -- every pixel is used exactly once, straight out of the register it was loaded into, so the detour
+// through shared memory (one issuing thread, an mbarrier round trip, an LDS per vector) only adds latency.  Kept
+// behind SEG_TMA for the record; the product builds with SEG_TMA = 0.
+#ifndef SEG_TMA
+#define SEG_TMA 0
+#endif
+__device__ __forceinline__ uint32_t seg_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void seg_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(seg_smem(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void seg_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(seg_smem(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void seg_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(seg_smem(dst)), "l"(src), "r"(bytes),
+               "r"(seg_smem(bar))
+               : "memory");
+}
+__device__ __forceinline__ void seg_mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(seg_smem(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+
 // 8 pixels of a uint4 against the threshold -> 8 bits
 __device__ __forceinline__ uint32_t seg_cmp8(const uint4& q, uint32_t t) {
   uint32_t m = 0;
@@ -100,7 +130,16 @@ __global__ void __launch_bounds__(SEG_THREADS, SEG_MINBLOCKS)
   constexpr int NWORDS = SEG_TR * SEG_TW;
   __shared__ int s_lbase;
   __shared__ uint32_t raw[SEG_RR][SEG_RW];
+#if SEG_TMA
+  // The staged pixel rows (TMA destination) and the union-find slots never live at the same time: the pixels are dead
+  // once the raw bits are packed (first barrier), the slots are born after it.  One buffer serves both.
+  constexpr int STAGE_BYTES = SEG_RR * 32 * SEG_TW * 2, SLOT_BYTES = NWORDS * SEG_SPW * 4;
+  __shared__ __align__(128) unsigned char stage_or_slots[STAGE_BYTES > SLOT_BYTES ? STAGE_BYTES : SLOT_BYTES];
+  __shared__ __align__(8) uint64_t mbar;
+  int* sp = reinterpret_cast<int*>(stage_or_slots);
+#else
   __shared__ int sp[NWORDS * SEG_SPW];
+#endif
   __shared__ uint32_t fsm[NWORDS], ssm[NWORDS];
   __shared__ unsigned short items[NWORDS];
   __shared__ int nitems;
@@ -116,6 +155,26 @@ __global__ void __launch_bounds__(SEG_THREADS, SEG_MINBLOCKS)
   const bool fast = x0 + 32 * SEG_TW <= W && (W & 7) == 0 && ((((uintptr_t)src) & 15) == 0);
   if (fast) {
     constexpr int RPW = SEG_RR / 4;  // rows per warp
+#if SEG_TMA
+    // One thread arms the barrier with the byte count and issues one 512-byte bulk copy per staged row; the SM's copy
+    // engine lands the rows in shared memory (UBLKCP), every thread waits on the mbarrier and reads its 8 pixels back.
+    uint16_t (*pix)[32 * SEG_TW] = reinterpret_cast<uint16_t (*)[32 * SEG_TW]>(stage_or_slots);
+    const int r_lo = max(2 - halo, 2 - y0), r_hi = min(SEG_TR + 2 + halo, H - y0 + 2);  // staged rows [r_lo, r_hi) lie in the image
+    if (tid == 0) seg_mbar_init(&mbar, 1);
+    __syncthreads();
+    if (tid == 0) {
+      seg_mbar_expect_tx(&mbar, (uint32_t)(r_hi - r_lo) * 32 * SEG_TW * 2);
+      for (int r = r_lo; r < r_hi; ++r) seg_bulk_g2s(&pix[r][0], src + (long long)(y0 - 2 + r) * W + x0, 32 * SEG_TW * 2, &mbar);
+    }
+    seg_mbar_wait(&mbar, 0);
+    uint4 q[RPW];
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+      const int r = wq + 4 * i;
+      q[i] = make_uint4(0, 0, 0, 0);
+      if (r >= r_lo && r < r_hi) q[i] = *reinterpret_cast<const uint4*>(&pix[r][lane * 8]);
+    }
+#else
     uint4 q[RPW];
 #pragma unroll
     for (int i = 0; i < RPW; ++i) {
@@ -123,6 +182,7 @@ __global__ void __launch_bounds__(SEG_THREADS, SEG_MINBLOCKS)
       q[i] = make_uint4(0, 0, 0, 0);
       if (r >= 2 - halo && r < SEG_TR + 2 + halo && yi >= 0 && yi < H) q[i] = __ldg(reinterpret_cast<const uint4*>(src + (long long)yi * W + x0) + lane);
     }
+#endif
 #pragma unroll
     for (int i = 0; i < RPW; ++i) {
       const int r = wq + 4 * i;
