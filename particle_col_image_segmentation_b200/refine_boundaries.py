@@ -51,3 +51,13 @@ def refine_boundaries(boundary_map, threshold=0.5, run_watershed=False, return_s
         if return_sweeps:
             out["sweeps"] = sweeps  # relaxation sweeps the flood took (diagnostic; not a reference output)
     return out
+
+
+def refine_boundaries_h5(file_path, channel=3, dataset="exported_data", **kwargs):
+    """refine_boundaries.py:28-34: load ``exported_data`` from the ilastik probability export, take the boundary channel
+    (channel-first, index 3 in the reference) and run ``refine_boundaries`` on it."""
+    from . import h5_io
+
+    with h5_io.File(file_path, "r") as f:
+        probabilities = np.array(f[dataset])
+    return refine_boundaries(probabilities[channel], **kwargs)

@@ -418,3 +418,17 @@ def process_single_array(ds_arr, cell_types):
         "recreated": ds_arr_recreated,
         "particle_area": particle_area,
     }
+
+
+def load_class_image(full_file_path):
+    """The read at the top of ``process_single_h5_file`` / ``process_multiple_h5_files`` (tiff_analysis.py:118-121,
+    :639-642): the first dataset of the ilastik export, squeezed to 2-D.  ``h5_io`` stands in for h5py, which is not
+    installable here (its compatibility with files written by libhdf5 itself is unverified, see ``h5_io``)."""
+    from . import h5_io
+
+    return normalize_ds_arr(h5_io.read_first_dataset(full_file_path))
+
+
+def process_single_h5_file(full_file_path, cell_types):
+    """tiff_analysis.py:627-671 without the plots and CSV files: read the export, then ``process_single_array``."""
+    return process_single_array(load_class_image(full_file_path), cell_types)

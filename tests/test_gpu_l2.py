@@ -229,3 +229,21 @@ def test_nanosims_imresize_and_resized_roi_sums():
         want = onano.analyse(planes, red, green, agg)
         assert got.shape == want.shape and got.shape[0] > 4
         np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-9, equal_nan=True)
+
+
+def test_h5_entry_points(tmp_path, ta):
+    """File -> result through the ilastik export reader: same answers as the array entry points."""
+    from particle_col_image_segmentation_b200 import h5_io, refine_boundaries as rb
+
+    img = synth.class_image(256, 256, seed=12)
+    p = h5_io.write_dataset(str(tmp_path / "seg.h5"), img[:, :, None], chunks=(64, 64, 1), compression="gzip")
+    types = {1: "C3M10", 2: "Particle", 3: "Background"}
+    got = ta.process_single_h5_file(p, types)
+    want = ta.process_single_array(img, types)
+    assert np.array_equal(got["recreated"], want["recreated"]) and got["cell_count"] == want["cell_count"] and got["particle_area"] == want["particle_area"]
+    _, prob = synth.touching_particles(160, 192, seed=4, pitch=32.0)
+    stack = np.stack([prob * 0, prob * 0, 1 - prob, prob]).astype(np.float32)
+    q = h5_io.write_dataset(str(tmp_path / "prob.h5"), stack, chunks=(1, 64, 64), compression="gzip", shuffle=True)
+    a, b = rb.refine_boundaries_h5(q), rb.refine_boundaries(prob)
+    for k in ("binary_mask", "distance", "local_max", "markers"):
+        assert np.array_equal(a[k], b[k]), k

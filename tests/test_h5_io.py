@@ -1,0 +1,101 @@
+"""ilastik ``.h5`` input path (tiff_analysis.py:118-120, :639-641; refine_boundaries.py:28-31) without h5py.
+
+h5py / libhdf5 are not installable in this image and no HDF5 file exists in it, so ``h5_io.File`` is checked
+against (1) files produced by this repo's own fixture writer in every layout the reader supports and (2) the
+byte positions the HDF5 File Format Specification gives for the structures the writer emits.  Compatibility with a
+file written by libhdf5 itself is therefore NOT verified here (see the module docstring)."""
+import struct
+
+import numpy as np
+import pytest
+
+from particle_col_image_segmentation_b200 import h5_io, synth
+
+
+@pytest.mark.parametrize("dtype", ["uint8", "uint16", "int32", "float32", "float64", ">u2", ">f4"])
+@pytest.mark.parametrize("layout", ["contiguous", "chunked", "gzip", "shuffle+gzip"])
+def test_roundtrip(tmp_path, dtype, layout):
+    rng = np.random.default_rng(1)
+    a = (rng.random((3, 37, 53)) * 200).astype(dtype)
+    kw = {}
+    if layout != "contiguous":
+        kw = dict(chunks=(1, 16, 32), compression="gzip" if "gzip" in layout else None, shuffle="shuffle" in layout)
+    p = h5_io.write_dataset(str(tmp_path / "x.h5"), a, **kw)
+    with h5_io.File(p) as f:
+        assert list(f.keys()) == ["exported_data"]
+        ds = f["exported_data"]
+        assert ds.shape == a.shape and ds.dtype == a.dtype
+        got = ds[()]
+        assert got.dtype == a.dtype and np.array_equal(got, a)
+        assert np.array_equal(np.array(ds), a) and np.array_equal(ds[1, 5:9], a[1, 5:9])
+
+
+def test_reference_call_pattern_on_a_class_image(tmp_path):
+    """``next(iter(f.keys()))`` + ``[()]`` on an ilastik-style (H, W, 1) uint8 class image, then normalize_ds_arr."""
+    img = synth.class_image(256, 320, seed=3)[:, :, None]
+    p = h5_io.write_dataset(str(tmp_path / "simple_seg.h5"), {"exported_data": img, "zz_other": np.arange(5)}, chunks=None)
+    with h5_io.File(p, "r") as f:
+        key = next(iter(f.keys()))
+        arr = f[key][()]
+    assert key == "exported_data" and arr.shape == (256, 320, 1) and np.array_equal(arr, img)
+    assert np.array_equal(h5_io.read_first_dataset(p), img)
+    from particle_col_image_segmentation_b200 import tiff_analysis
+
+    assert tiff_analysis.normalize_ds_arr(arr).shape == (256, 320)
+    with pytest.raises(KeyError):
+        with h5_io.File(p) as f:
+            f["missing"]
+
+
+def test_probability_stack_chunked_like_ilastik(tmp_path):
+    """refine_boundaries.py:29-34: ``np.array(f["exported_data"])`` is (C, H, W) float32; channel 3 is the boundary map."""
+    _, prob = synth.touching_particles(128, 160, seed=5, pitch=32.0)
+    stack = np.stack([prob * 0.1, prob * 0.2, 1 - prob, prob]).astype(np.float32)
+    p = h5_io.write_dataset(str(tmp_path / "probabilities.h5"), stack, chunks=(1, 64, 64), compression="gzip", shuffle=True)
+    with h5_io.File(p) as f:
+        got = np.array(f["exported_data"])
+    assert got.dtype == np.float32 and np.array_equal(got, stack) and np.array_equal(got[3], prob)
+
+
+def test_structures_sit_where_the_specification_puts_them(tmp_path):
+    a = np.arange(24, dtype="<u2").reshape(4, 6)
+    raw = open(h5_io.write_dataset(str(tmp_path / "s.h5"), a), "rb").read()
+    assert raw[:8] == b"\x89HDF\r\n\x1a\n" and raw[8] == 0          # format signature, superblock version 0
+    assert raw[13] == 8 and raw[14] == 8                              # size of offsets / lengths
+    assert struct.unpack_from("<HH", raw, 16) == (4, 16)             # group leaf / internal node K
+    base, free, eof, drv = struct.unpack_from("<QQQQ", raw, 24)
+    assert base == 0 and free == h5_io.UNDEF and eof == len(raw) and drv == h5_io.UNDEF
+    name_off, root_hdr, cache = struct.unpack_from("<QQI", raw, 56)  # root group symbol table entry
+    btree, heap = struct.unpack_from("<QQ", raw, 80)
+    assert cache == 1 and raw[btree : btree + 4] == b"TREE" and raw[heap : heap + 4] == b"HEAP"
+    assert raw[root_hdr] == 1                                          # version-1 object header ...
+    assert struct.unpack_from("<H", raw, root_hdr + 16)[0] == 0x11    # ... whose first message is the symbol table message
+    assert struct.unpack_from("<QQ", raw, root_hdr + 24) == (btree, heap)
+    snod = struct.unpack_from("<Q", raw, btree + 32)[0]               # child 0 of the root B-tree node
+    assert raw[snod : snod + 4] == b"SNOD" and struct.unpack_from("<H", raw, snod + 6)[0] == 1
+    link, hdr = struct.unpack_from("<QQ", raw, snod + 8)
+    data_seg = struct.unpack_from("<Q", raw, heap + 24)[0]
+    assert raw[data_seg + link : data_seg + link + 14] == b"exported_data\0"
+    types = []
+    p, end = hdr + 16, hdr + 16 + struct.unpack_from("<I", raw, hdr + 8)[0]
+    while p < end:
+        t, size = struct.unpack_from("<HH", raw, p)
+        types.append(t)
+        if t == 0x08:                                                  # contiguous layout: address and size of the raw data
+            ver, cls, addr, nbytes = struct.unpack_from("<BBQQ", raw, p + 8)
+            assert (ver, cls, nbytes) == (3, 1, a.nbytes) and raw[addr : addr + a.nbytes] == a.tobytes()
+        p += 8 + size
+    assert types == [0x01, 0x03, 0x08]
+
+
+def test_unsupported_files_fail_loudly(tmp_path):
+    p = tmp_path / "not.h5"
+    p.write_bytes(b"II*\0" + b"\0" * 600)
+    with pytest.raises(h5_io.H5Error):
+        h5_io.File(str(p))
+    q = h5_io.write_dataset(str(tmp_path / "v.h5"), np.zeros((4, 4), np.uint8))
+    raw = bytearray(open(q, "rb").read())
+    raw[8] = 7  # an unknown superblock version
+    (tmp_path / "v7.h5").write_bytes(bytes(raw))
+    with pytest.raises(h5_io.H5Error):
+        h5_io.File(str(tmp_path / "v7.h5"))
