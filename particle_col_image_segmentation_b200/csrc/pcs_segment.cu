@@ -226,27 +226,37 @@ __global__ void __launch_bounds__(SEG_THREADS, SEG_MINBLOCKS)
   if (k < WW) {
     const uint32_t vm = pcs_valid_mask(k, W);
     if (MEDIAN) {
-      uint32_t r0[6], r1[6], r2[6];  // bit-sliced horizontal counts of the six input rows
+      // the six input rows' windows first: nine pixels in ten are background, and a thread whose windows hold no set
+      // bit at all (bits 14 .. 49 are the ones the 5-wide sums look at) has two all-zero output words and skips the
+      // carry-save adders -- most of this phase's instructions
+      unsigned long long win[6];
+      unsigned long long seen = 0;
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
         const int yi = y0 + 2 * strip - 2 + i;  // input row
-        r0[i] = r1[i] = r2[i] = 0u;
+        win[i] = 0;
         if (yi - 2 < H) {  // still needed by an output row of the image
           const int ry = pcs_reflect(yi, H);
           const uint32_t* rowp = &raw[ry - (y0 - 2)][1] - k0;  // rowp[k'] = word k' of that row
           // words away from the left / right image border need no reflection: three shared loads and two funnel shifts
-          const unsigned long long win = inner ? ((unsigned long long)rowp[k] << 16) | (rowp[k - 1] >> 16) | ((unsigned long long)(rowp[k + 1] & 0xffffu) << 48)
-                                               : pcs_window_reflect(rowp, k, W, WW, 2);
-          pcs_add5((uint32_t)(win >> 14), (uint32_t)(win >> 15), (uint32_t)(win >> 16), (uint32_t)(win >> 17), (uint32_t)(win >> 18), r0[i],
-                   r1[i], r2[i]);
+          win[i] = inner ? ((unsigned long long)rowp[k] << 16) | (rowp[k - 1] >> 16) | ((unsigned long long)(rowp[k + 1] & 0xffffu) << 48)
+                         : pcs_window_reflect(rowp, k, W, WW, 2);
+          seen |= win[i];
         }
       }
+      if (seen & 0x0003ffffffffc000ull) {
+        uint32_t r0[6], r1[6], r2[6];  // bit-sliced horizontal counts of the six input rows
 #pragma unroll
-      for (int o = 0; o < 2; ++o) {
-        const uint32_t a0[5] = {r0[o], r0[o + 1], r0[o + 2], r0[o + 3], r0[o + 4]};
-        const uint32_t a1[5] = {r1[o], r1[o + 1], r1[o + 2], r1[o + 3], r1[o + 4]};
-        const uint32_t a2[5] = {r2[o], r2[o + 1], r2[o + 2], r2[o + 3], r2[o + 4]};
-        if (y0 + 2 * strip + o < H) fin[o] = pcs_majority5_word(a0, a1, a2) & vm;
+        for (int i = 0; i < 6; ++i)
+          pcs_add5((uint32_t)(win[i] >> 14), (uint32_t)(win[i] >> 15), (uint32_t)(win[i] >> 16), (uint32_t)(win[i] >> 17), (uint32_t)(win[i] >> 18),
+                   r0[i], r1[i], r2[i]);
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+          const uint32_t a0[5] = {r0[o], r0[o + 1], r0[o + 2], r0[o + 3], r0[o + 4]};
+          const uint32_t a1[5] = {r1[o], r1[o + 1], r1[o + 2], r1[o + 3], r1[o + 4]};
+          const uint32_t a2[5] = {r2[o], r2[o + 1], r2[o + 2], r2[o + 3], r2[o + 4]};
+          if (y0 + 2 * strip + o < H) fin[o] = pcs_majority5_word(a0, a1, a2) & vm;
+        }
       }
     } else {
 #pragma unroll

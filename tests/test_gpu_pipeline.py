@@ -207,3 +207,27 @@ def test_refine_labeled_matches_scipy(seg, min_size):
             want = ndi.binary_fill_holes(remove_small_objects(m[i], min_size=min_size, connectivity=2))
             assert np.array_equal(got[i], want), (m.shape, i, np.argwhere(got[i] != want)[:5])
         assert np.array_equal(mask.cpu().numpy().astype(bool), got)
+
+
+def test_first_call_on_two_streams_in_a_fresh_process(seg):
+    """The EDT's sqrt table used to be filled lazily on the caller's stream: a first call that spread its chunks over two
+    streams (or ran inside a graph capture) could read the table before it was written.  The table is a compile-time
+    constant now; this runs exactly that first call in a fresh process and compares every output with the oracle."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import numpy as np, torch\n"
+        "from oracle import pipeline as opipe\n"
+        "from particle_col_image_segmentation_b200 import split_zstack, synth\n"
+        "stack = synth.zstack_u16(4, 96, 160, seed=19)\n"
+        "got = split_zstack.SegmentPlan(torch.from_numpy(stack).cuda(), chunk=1, streams=2, graph=False)().to_numpy()\n"
+        "want = opipe.segment_zstack(stack)\n"
+        "assert all(np.array_equal(got[k], want[k]) for k in ('threshold', 'mask', 'labels', 'refined', 'edt', 'table')), 'first call differs'\n"
+        "print('first call ok')\n"
+    ) % root
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "first call ok" in out.stdout, out.stdout[-1500:] + out.stderr[-1500:]
