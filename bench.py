@@ -63,13 +63,17 @@ KERNEL_BYTES_PER_VOXEL = {
 
 # DRAM traffic per voxel of the dominant kernels from the `ncu --set full` capture of profiles/prof_step.py
 # (16 slices of 2048^2 per launch; dram__bytes_read.sum + dram__bytes_write.sum over 67.1 Mvoxel), see
-# profiles/r1k_ncu_full_summary.txt.  Below the algorithmic figure where part of the output is still in L2
+# profiles/r2_ncu_full_summary.txt.  Below the algorithmic figure where part of the output is still in L2
 # when the kernel ends.
+NCU_TRAFFIC_SOURCE = "profiles/r2_ncu_full_summary.txt"
 NCU_TRAFFIC_BYTES_PER_VOXEL = {
-    "k_edt_near": (16.81 + 480.48) / 67.109,
-    "k_hist_u16": (136.02 + 4.80) / 67.109,
-    "k_ccl_relabel": (60.45 + 209.11) / 67.109,
+    "k_edt_near": (16.81 + 483.27) / 67.109,
+    "k_hist_u16": (136.16 + 4.60) / 67.109,
+    "k_seg_threshold_tile": (142.47 + 62.83) / 67.109,
+    "k_ccl_relabel": (18.27 + 211.89) / 67.109,
+    "k_refine_rows": (18.44 + 26.25) / 67.109,
 }
+NCU_TRAFFIC_WHOLE_STEP_BYTES_PER_VOXEL = (431.6 + 788.9) / 67.109  # every kernel of the step: 18.2 B/voxel (round 1: 21.8; algorithmic: 16)
 
 
 def write_only_probe(dev, lib):
@@ -486,7 +490,7 @@ def run_b200(args):
         achieved = bpv * per_launch_vox / (avg_ms * 1e-3) / 1e9
         tpv = NCU_TRAFFIC_BYTES_PER_VOXEL.get(name)
         roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": (tpv * per_launch_vox if tpv else None), "traffic_source": "ncu --set full, profiles/r1k_ncu_full_summary.txt (per voxel, scaled to this launch)" if tpv else None,
+                "traffic": (tpv * per_launch_vox if tpv else None), "traffic_source": f"ncu --set full, {NCU_TRAFFIC_SOURCE} (per voxel, scaled to this launch)" if tpv else None,
                 "write_only_gbs_live": write_only_probe(dev, lib),
                 "bytes_per_voxel": bpv, "avg_launch_ms": avg_ms, "launches": kcnt, "peak_source": peak_src, "kernel_time_share": shares,
                 "kernel_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
@@ -514,7 +518,8 @@ def run_b200(args):
         "gpu_launches": int(launches),
         "roofline": roof,
         "pipeline_roofline": {"bytes_per_voxel": PIPELINE_BYTES_PER_VOXEL, "achieved_gbs_per_gpu": per_gpu * PIPELINE_BYTES_PER_VOXEL / 1e9, "frac_of_peak": per_gpu * PIPELINE_BYTES_PER_VOXEL / 1e9 / peak,
-                              "sum_of_stages_frac": per_gpu * SUM_OF_STAGES_BYTES_PER_VOXEL / 1e9 / peak},
+                              "sum_of_stages_frac": per_gpu * SUM_OF_STAGES_BYTES_PER_VOXEL / 1e9 / peak,
+                              "dram_traffic_bytes_per_voxel_ncu": NCU_TRAFFIC_WHOLE_STEP_BYTES_PER_VOXEL, "traffic_source": NCU_TRAFFIC_SOURCE},
         "cpu_baseline": cpu,
     }
     print(json.dumps(line))
