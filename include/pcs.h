@@ -67,6 +67,11 @@ int pcs_gather(const void* img, int dtype, const int64_t* slice, const int64_t* 
 
 /* dst[i] = value for n_words uint32 (multiple of 4, dst 16-byte aligned): grid-stride 128-bit stores; doubles as
  * the store-only bandwidth probe of bench.py */
+/* *out (device int64) = largest label of an int32 / int64 label image (0 for an empty one): regionprops on a label image
+ * whose label count is not known (tiff_analysis.py:263, :746 pass label images straight from label()) */
+int pcs_max_label(const void* labels, int label_bytes, int64_t n, int64_t* out, void* stream);
+/* out (W, H) = in (H, W) transposed, elem_bytes 1 or 4: MATLAB numbers components in column-major order (.m:104, :173) */
+int pcs_transpose(const void* in, void* out, int elem_bytes, int H, int W, void* stream);
 int pcs_fill_u32(void* dst, uint32_t value, size_t n_words, void* stream);
 /* zero `bytes` (multiple of 32, 32-byte aligned) with a small persistent grid (ctas_per_sm CTAs of 128 threads per SM):
  * for a side stream, beside kernels that leave DRAM idle */

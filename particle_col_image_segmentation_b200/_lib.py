@@ -41,6 +41,8 @@ SIGNATURES = {
     "pcs_lut_u8": (c_int, [_P, _P, _L, _P]),
     "pcs_assign_where_u8": (c_int, [_P, _P, _I, _I, _I, _I, _P]),
     "pcs_gather": (c_int, [_P, _I, _P, _P, _P, _L, _L, _P]),
+    "pcs_max_label": (c_int, [_P, _I, _L, _P, _P]),
+    "pcs_transpose": (c_int, [_P, _P, _I, _I, _I, _P]),
     "pcs_fill_u32": (c_int, [_P, c_uint32, _Z, _P]),
     "pcs_zero_background": (c_int, [_P, _Z, _I, _P]),
     "pcs_histogram_bytes": (_Z, [_I]),

@@ -273,6 +273,29 @@ __global__ void __launch_bounds__(256) k_fill128(uint4* __restrict__ p, uint32_t
   for (; i < n16; i += stride) p[i] = make_uint4(v, v, v, v);
 }
 
+// largest label of an int32 / int64 label image (regionprops on a label image whose label count is not known)
+template <typename T>
+__global__ void __launch_bounds__(256) k_max_label(const T* __restrict__ lab, long long n, long long* __restrict__ out) {
+  long long m = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) m = max(m, (long long)lab[i]);
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+
+// out (W, H) = in (H, W) transposed, 1- or 4-byte elements (MATLAB's column-major component order = raster order of
+// the transposed mask, nanosims.matlab_label); 32 x 32 tiles through shared memory
+template <typename T>
+__global__ void __launch_bounds__(256) k_transpose(const T* __restrict__ in, T* __restrict__ out, int H, int W) {
+  __shared__ T tile[32][33];
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8)
+    if (y0 + r < H && x0 + tx < W) tile[r][tx] = in[(long long)(y0 + r) * W + x0 + tx];
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8)
+    if (x0 + r < W && y0 + tx < H) out[(long long)(x0 + r) * H + y0 + tx] = tile[tx][r];
+}
+
 extern "C" {
 
 int pcs_compare_u16(const uint16_t* img, int thr, const int32_t* thr_dev, int cmp, uint32_t* bits, uint8_t* mask, int B,
@@ -418,6 +441,32 @@ int pcs_fill_u32(void* dst, uint32_t value, size_t n_words, void* stream) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   PCS_LAUNCH("k_fill128", (cudaStream_t)stream, k_fill128<<<sms * 16, 256, 0, (cudaStream_t)stream>>>((uint4*)dst, value, n_words / 4));
   return pcs_check_launch("fill");
+}
+
+int pcs_max_label(const void* labels, int label_bytes, int64_t n, int64_t* out, void* stream) {
+  PCS_REQUIRE(labels && out && n >= 0, "bad arguments");
+  PCS_REQUIRE(label_bytes == 4 || label_bytes == 8, "label dtype must be int32 or int64");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(out, 0, 8, st);
+  if (n == 0) return PCS_OK;
+  const unsigned g = pcs_blocks(n, 256 * 8);
+  if (label_bytes == 4)
+    PCS_LAUNCH("k_max_label", st, k_max_label<int32_t><<<g, 256, 0, st>>>((const int32_t*)labels, n, (long long*)out));
+  else
+    PCS_LAUNCH("k_max_label", st, k_max_label<long long><<<g, 256, 0, st>>>((const long long*)labels, n, (long long*)out));
+  return pcs_check_launch("max label");
+}
+
+int pcs_transpose(const void* in, void* out, int elem_bytes, int H, int W, void* stream) {
+  PCS_REQUIRE(in && out && in != out && H >= 1 && W >= 1, "bad arguments");
+  PCS_REQUIRE(elem_bytes == 1 || elem_bytes == 4, "transpose handles 1- and 4-byte elements");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 g((W + 31) / 32, (H + 31) / 32);
+  if (elem_bytes == 1)
+    PCS_LAUNCH("k_transpose", st, k_transpose<uint8_t><<<g, 256, 0, st>>>((const uint8_t*)in, (uint8_t*)out, H, W));
+  else
+    PCS_LAUNCH("k_transpose", st, k_transpose<uint32_t><<<g, 256, 0, st>>>((const uint32_t*)in, (uint32_t*)out, H, W));
+  return pcs_check_launch("transpose");
 }
 
 }  // extern "C"

@@ -149,7 +149,7 @@ def region_table_host(label_image, intensity_image=None, overlap_mask=None, n_la
             raise TypeError("Non-integer label_image types are ambiguous")
         lab = lab.to(torch.int32)
     if n_labels is None:
-        n_labels = int(lab.max().item()) if lab.numel() else 0
+        n_labels = ops.max_label(lab) if lab.numel() else 0
     cap = max(1, n_labels)
     table = ops.new_table(cap, lab.device)
     inten = None

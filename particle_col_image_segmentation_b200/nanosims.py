@@ -30,10 +30,10 @@ def matlab_label(mask):
     t = _io.image_2d(mask)
     if t.dtype == torch.bool:
         t = t.view(torch.uint8)
-    tt = t[0].t().contiguous().unsqueeze(0)
+    tt = ops.transpose2d(t[0]).unsqueeze(0)
     bits = ops.compare(tt, "!=", 0)[0]
     lab, counts, _ = ops.label_bits(bits, int(tt.shape[2]), connectivity=8, dtype=torch.int32)
-    return lab[0].t().contiguous(), int(counts[0].item())
+    return ops.transpose2d(lab[0]), int(counts[0].item())
 
 
 def _cubic(x):
@@ -154,8 +154,8 @@ def boundary_pixels(mask):
     cross = np.array([[0, 1, 0], [1, 1, 1], [0, 1, 0]], dtype=np.uint8)
     inner = ops.erode(bits, W, cross, border_value=0)
     edge = ops.logic(bits, inner, "andnot", W)
-    m = ops.unpack(edge, W, torch.bool)[0]
-    return (torch.nonzero(m).to(torch.float64) + 1.0).contiguous()  # nonzero() hands back a transposed view
+    m = ops.unpack(edge, W, torch.uint8)[0].cpu().numpy()  # a few hundred pixels of a 256^2 mask: listed on the host
+    return torch.from_numpy(np.argwhere(m).astype(np.float64) + 1.0).to(bits.device)
 
 
 def analyse(planes, red_mask, green_mask, agg_mask, raster=19.0, acq=512.0):

@@ -147,6 +147,24 @@ def assign_where_u8_(img, bits, value):
     return img
 
 
+def max_label(labels):
+    """Largest label of an int32 / int64 label image (one reduction kernel, one read-back)."""
+    out = torch.empty(1, dtype=torch.int64, device=labels.device)
+    _lib.call("pcs_max_label", _p(labels), 4 if labels.dtype == torch.int32 else 8, int(labels.numel()), _p(out), _stream())
+    return int(out.item())
+
+
+def transpose2d(t):
+    """(H, W) uint8 / bool / int32 CUDA tensor -> contiguous (W, H) transpose."""
+    H, W = (int(v) for v in t.shape)
+    src = t.view(torch.uint8) if t.dtype == torch.bool else t
+    if src.element_size() not in (1, 4):
+        raise _lib.PcsError(f"transpose2d: unsupported dtype {t.dtype}")
+    out = torch.empty((W, H), dtype=src.dtype, device=t.device)
+    _lib.call("pcs_transpose", _p(src.contiguous()), _p(out), src.element_size(), H, W, _stream())
+    return out
+
+
 def gather(img, slice_idx, lin_idx):
     """``img[slice_idx, lin_idx]`` over flattened slices -> int64."""
     n = int(lin_idx.numel())
