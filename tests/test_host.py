@@ -124,6 +124,17 @@ nBs = [None] * world
 dist.all_gather_object(nBs, int(local.shape[0] - cut))
 assert out4.shape == (world * (cap - 1) + sum(nBs), 13), out4.shape
 assert out4[0, 0].item() == 0.0 and out4[cap - 1 + nBs[0], 0].item() == 1000.0   # rank 1's rows follow rank 0's two chunks
+# the copy-free form: a producer writes rows + count straight into a message buffer (what SegmentPlan(staging=...) does)
+seen = [None] * world
+dist.all_gather_object(seen, [cut, int(local.shape[0] - cut)])
+stages = tg.make_staging([max(s[0] for s in seen), max(s[1] for s in seen)], [cap, cap], 13, "cpu", n=2)  # counts reduced over the ranks: every rank ships the same message size
+for it in range(3):
+    st = stages[it % 2]
+    st.rows[0][:cut] = local[:cut]; st.counts[0][0] = cut
+    st.rows[1][: local.shape[0] - cut] = local[cut:]; st.counts[1][0] = local.shape[0] - cut
+    got = tg.exchange(st).compact()
+    assert (got is None) if rank != 0 else np.array_equal(got.numpy(), full), rank
+assert stages[0].hdr_rows == 1 and stages[0].buf.shape[0] == 1 + sum(stages[0].caps)
 # a count above the TABLE capacity is an error of its own (silent truncation otherwise)
 try:
     pdist.gather_tables_padded(padded, torch.tensor([0, cap + 5], dtype=torch.int32))
