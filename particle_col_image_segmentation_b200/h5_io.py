@@ -444,6 +444,46 @@ def _object_header(msgs):
     return struct.pack("<BBHII", 1, 0, len(msgs), 1, len(body)) + b"\0" * 4 + body
 
 
+def write_dataset_v2(path, arrays):
+    """The same content in the newer structures (what ``libver="latest"`` groups look like): superblock version 2, a root
+    group whose version-2 object header ("OHDR") carries one link message per dataset, version-2 dataset headers with a
+    version-2 dataspace and a contiguous version-3 layout.  Checksum fields are left zero (the reader does not verify
+    them).  Fixture for the reader's second code path."""
+    if isinstance(arrays, np.ndarray):
+        arrays = {"exported_data": arrays}
+    names = sorted(arrays)
+    out = bytearray(b"\0" * 48)  # superblock v2: 8 + 4 + 4 x 8 + 4
+
+    def put(blob):
+        while len(out) % 8:
+            out.append(0)
+        at = len(out)
+        out.extend(blob)
+        return at
+
+    def ohdr(msgs):
+        body = b"".join(struct.pack("<BHB", t, len(d), 0) + d for t, d in msgs)
+        return b"OHDR" + bytes([2, 0x02]) + struct.pack("<I", len(body)) + body + b"\0" * 4  # flags 0x02: 4-byte chunk size; checksum 0
+
+    headers = {}
+    for nm in names:
+        a = np.ascontiguousarray(arrays[nm])
+        data_at = put(a.tobytes())
+        space = struct.pack("<BBBB", 2, a.ndim, 0, 1) + b"".join(struct.pack("<Q", s) for s in a.shape)
+        headers[nm] = put(ohdr([(0x01, space), (0x03, _dtype_msg(a.dtype)), (0x08, struct.pack("<BBQQ", 3, 1, data_at, a.nbytes))]))
+    links = []
+    for nm in names:
+        raw = nm.encode("utf-8")
+        links.append((0x06, struct.pack("<BBB", 1, 0, len(raw)) + raw + struct.pack("<Q", headers[nm])))  # version 1, flags 0: hard link, 1-byte name length
+    root = put(ohdr(links))
+    eof = len(out)
+    sb = SIGNATURE + bytes([2, 8, 8, 0]) + struct.pack("<QQQQ", 0, UNDEF, eof, root) + b"\0" * 4
+    out[: len(sb)] = sb
+    with open(path, "wb") as fh:
+        fh.write(bytes(out))
+    return path
+
+
 def write_dataset(path, arrays, chunks=None, compression=None, shuffle=False):
     """Write ``{name: array}`` (or a single array under ``"exported_data"``) as datasets of the root group of a new
     file: superblock 0, symbol-table group, version-1 object headers, layout version 3 -- contiguous, or chunked

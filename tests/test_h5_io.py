@@ -99,3 +99,18 @@ def test_unsupported_files_fail_loudly(tmp_path):
     (tmp_path / "v7.h5").write_bytes(bytes(raw))
     with pytest.raises(h5_io.H5Error):
         h5_io.File(str(tmp_path / "v7.h5"))
+
+
+def test_newer_structures_superblock2_ohdr_links(tmp_path):
+    """Superblock version 2, version-2 object headers, link messages instead of a symbol table, version-2 dataspace."""
+    a = np.arange(5 * 7, dtype=np.int32).reshape(5, 7) - 9
+    b = np.linspace(0, 1, 12).reshape(3, 4)
+    p = h5_io.write_dataset_v2(str(tmp_path / "v2.h5"), {"exported_data": a, "other": b})
+    raw = open(p, "rb").read()
+    assert raw[8] == 2 and raw[9] == 8 and raw[10] == 8                      # superblock version, offset / length sizes
+    root = struct.unpack_from("<Q", raw, 36)[0]
+    assert raw[root : root + 4] == b"OHDR" and raw[root + 4] == 2            # version-2 root object header
+    with h5_io.File(p) as f:
+        assert list(f.keys()) == ["exported_data", "other"] and "other" in f
+        assert np.array_equal(f["exported_data"][()], a) and f["exported_data"].dtype == np.int32
+        assert np.array_equal(np.array(f["other"]), b)
