@@ -844,7 +844,14 @@ __global__ void __launch_bounds__(REFINE_MAX_WARPS * 32)
     for (int u = 0; u < 4; ++u) {
       const int k = kb + 32 * u + lane;
       L4[u] = 0;
-      if (f4[u]) L4[u] = PLANES ? -lpl[k] : __ldg(lrow + (k << 5) + __ffs(f4[u]) - 1);
+      if (PLANES) {
+        // plane 0 holds the label of the word's first run: requested for every word of the row beside the word itself
+        // (one coalesced line per 32 words either way; what it holds for an empty word is never used), so the
+        // word -> label -> area chain is two round trips, not three
+        if (k < WW) L4[u] = -lpl[k];
+      } else if (f4[u]) {
+        L4[u] = __ldg(lrow + (k << 5) + __ffs(f4[u]) - 1);
+      }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -939,16 +946,28 @@ __global__ void __launch_bounds__(REFINE_MAX_WARPS * 32)
   // without painting, and such rows leave with an all-zero candidate row -- no scratch to clear, no prefix scan.
   int fb = -1;  // end of the row prefix painted when a search window ran out
   bool pair = false;
-  for (int i = lane; i < n; i += 32) {
-    const int L = rl[i];
-    const int lo = max(i - REFINE_K, 0);
-    int j = i - 1;
-    while (j >= lo && rl[j] != L) --j;
-    const int e = (int)(rse[i] & 0xffffu) - 1;
-    if (j >= lo) {
-      pair |= (int)(rse[j] >> 16) + 1 <= e;
-    } else if (lo > 0) {
-      fb = max(fb, e);
+  // Up to 32 kept runs (the usual row has about ten): one __match_any_sync over the labels gives every run the lanes
+  // that hold the same label, the nearest one below is its partner -- no backward walk (which cost each lane as many
+  // steps as there were runs before it, and the warp as many as the row had runs)
+  const bool small = n <= 32;
+  int jm = -1;  // partner of run `lane` when small
+  if (small) {
+    const int L = lane < n ? rl[lane] : -(lane + 1);  // idle lanes: distinct negative sentinels (labels are positive)
+    const unsigned same = __match_any_sync(0xffffffffu, L) & ((1u << lane) - 1u);
+    jm = same ? 31 - __clz(same) : -1;
+    if (lane < n && jm >= 0) pair = (int)(rse[jm] >> 16) + 1 <= (int)(rse[lane] & 0xffffu) - 1;
+  } else {
+    for (int i = lane; i < n; i += 32) {
+      const int L = rl[i];
+      const int lo = max(i - REFINE_K, 0);
+      int j = i - 1;
+      while (j >= lo && rl[j] != L) --j;
+      const int e = (int)(rse[i] & 0xffffu) - 1;
+      if (j >= lo) {
+        pair |= (int)(rse[j] >> 16) + 1 <= e;
+      } else if (lo > 0) {
+        fb = max(fb, e);
+      }
     }
   }
   if (!__any_sync(0xffffffffu, pair || fb >= 0)) {
@@ -961,15 +980,22 @@ __global__ void __launch_bounds__(REFINE_MAX_WARPS * 32)
   }
   if (lane == 0) diff[WW] = 0;
   __syncwarp();
-  for (int i = lane; i < n; i += 32) {
-    const int L = rl[i];
-    const int lo = max(i - REFINE_K, 0);
-    int j = i - 1;
-    while (j >= lo && rl[j] != L) --j;
-    const int e = (int)(rse[i] & 0xffffu) - 1;
-    if (j >= lo) {
-      const int a = (int)(rse[j] >> 16) + 1;
+  if (small) {
+    if (lane < n && jm >= 0) {
+      const int a = (int)(rse[jm] >> 16) + 1, e = (int)(rse[lane] & 0xffffu) - 1;
       if (a <= e) refine_paint(cb, diff, a, e);
+    }
+  } else {
+    for (int i = lane; i < n; i += 32) {
+      const int L = rl[i];
+      const int lo = max(i - REFINE_K, 0);
+      int j = i - 1;
+      while (j >= lo && rl[j] != L) --j;
+      const int e = (int)(rse[i] & 0xffffu) - 1;
+      if (j >= lo) {
+        const int a = (int)(rse[j] >> 16) + 1;
+        if (a <= e) refine_paint(cb, diff, a, e);
+      }
     }
   }
   fb = __reduce_max_sync(0xffffffffu, fb);
