@@ -240,7 +240,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.01)  # ~100 Hz: a tight NVML polling loop in every rank contended with the ranks' own launches
+            time.sleep(0.002)  # a few hundred Hz (an NVML query takes about a millisecond itself), on rank 0 only
 
     def start(self):
         if self.ok:
