@@ -483,11 +483,14 @@ __global__ void __launch_bounds__(PCS_CCL_THREADS)
   const int* par = parent + b * ((long long)NW << LSPW);
   if (k < WW) {
     P p = prov.slice(b);
-    p.FS(y, k, F, S);
     const int gw = y * WW + k;
+    // plane 0 (the first run of the word) is requested beside the word itself: one coalesced line per 32 words, and the
+    // word -> parent chain loses a round trip (what the plane holds for an empty word is never used)
+    const int p0pre = par[gw];
+    p.FS(y, k, F, S);
     uint32_t rem = S;
     if (rem && !(rem & (rem - 1))) {
-      const int p0 = par[gw];  // plane 0: the word's only run
+      const int p0 = p0pre;  // plane 0: the word's only run
       one = p0 < 0 ? -p0 : -par[pcs_slot<LSPW>(p0, NW)];
       rem = 0;
     }

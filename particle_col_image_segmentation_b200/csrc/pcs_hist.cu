@@ -64,9 +64,12 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MINBLOCKS)
   for (int i = 0; i < 32768 / 4 / HIST_THREADS; ++i) sh4[tid + i * HIST_THREADS] = make_uint4(0, 0, 0, 0);
   // tiles [g0, g1) of the flattened space belong to this CTA
   const long long g0 = total_tiles * blockIdx.x / gridDim.x, g1 = total_tiles * (blockIdx.x + 1) / gridDim.x;
-  auto tile_src = [&](long long g, long long& start) {
-    const long long b = g / ntiles;
-    start = (g - b * ntiles) * HIST_PIX_PER_BLOCK;
+  // (slice, tile) of a flattened tile index; the walk below advances it incrementally (a 64-bit division per tile and
+  // thread was an eighth of this kernel's instructions)
+  long long cur_b = g0 / ntiles;
+  int cur_t = (int)(g0 - cur_b * ntiles);
+  auto tile_at = [&](long long b, int t, long long& start) {
+    start = (long long)t * HIST_PIX_PER_BLOCK;
     return img + b * npix;
   };
   auto full_tile = [&](const uint16_t* src, long long start) {
@@ -75,7 +78,7 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MINBLOCKS)
   uint4 cur[HIST_VEC_PER_THREAD];
   if (g0 < g1) {
     long long start;
-    const uint16_t* src = tile_src(g0, start);
+    const uint16_t* src = tile_at(cur_b, cur_t, start);
     if (full_tile(src, start)) {
       const uint4* s4 = reinterpret_cast<const uint4*>(src + start) + tid;
 #pragma unroll
@@ -85,10 +88,15 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MINBLOCKS)
   __syncthreads();
   for (long long g = g0; g < g1; ++g) {
     long long start, nstart = 0;
-    const uint16_t* src = tile_src(g, start);
+    const uint16_t* src = tile_at(cur_b, cur_t, start);
     const uint16_t* nsrc = src;
     const bool more = g + 1 < g1;
-    if (more) nsrc = tile_src(g + 1, nstart);
+    const long long this_b = cur_b;
+    if (++cur_t == ntiles) {  // the next tile opens the next slice
+      cur_t = 0;
+      ++cur_b;
+    }
+    if (more) nsrc = tile_at(cur_b, cur_t, nstart);
     const bool have_next = more && full_tile(nsrc, nstart);
     if (full_tile(src, start)) {
       const uint4* n4 = reinterpret_cast<const uint4*>(nsrc + nstart) + tid;
@@ -121,7 +129,7 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MINBLOCKS)
     }
     if (!__syncthreads_or(hot | (int)last)) continue;
     // flush the non-zero counters into the slice's histogram and clear them
-    uint32_t* gh = hist + (g / ntiles) * 65536;
+    uint32_t* gh = hist + this_b * 65536;
 #pragma unroll
     for (int i = 0; i < 32768 / 4 / HIST_THREADS; ++i) {
       const int idx = tid + i * HIST_THREADS;

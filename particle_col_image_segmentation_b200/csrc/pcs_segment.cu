@@ -435,12 +435,13 @@ __global__ void __launch_bounds__(SEG_LIST_THREADS)
   const int* wl = wlist + b * (long long)NW;
   for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < n; it += gridDim.x * blockDim.x) {
     const int gw = wl[it];
+    const int q0 = pcs_ld_cg(par + gw);  // plane 0, requested beside the word: a listed word has at least one run
     const uint32_t F = __ldg(bb + gw);
     const int nr = __popc(F & ~(F << 1));
     uint32_t roots = 0;
     for (int j = 0; j < nr; ++j) {
       const int nd = pcs_node<SEG_LSPW>(gw, j);
-      int r = nd, q = pcs_ld_cg(par + j * NW + gw);
+      int r = nd, q = j == 0 ? q0 : pcs_ld_cg(par + j * NW + gw);
       const int first = q;
       while (q != r) {
         r = q;
@@ -799,6 +800,7 @@ __global__ void __launch_bounds__(SEG_LIST_THREADS)
     int l0 = 0, area = 0, sy = 0, sx = 0, si = 0, minx = 0x7fffffff, maxx = -1, y = 0;
     if (valid) {
       const int gw = wl[it];
+      const int p00 = par[gw], rs00 = rs[gw];  // plane 0 of both, requested beside the word
       const uint32_t F = __ldg(bb + gw);
       y = gw / WW;
       const int x0 = (gw - y * WW) << 5;
@@ -806,8 +808,8 @@ __global__ void __launch_bounds__(SEG_LIST_THREADS)
       for (int j = 0; S; ++j) {
         int s;
         const uint32_t R = pcs_pop_run(F, S, s);
-        const int p0 = par[j * NW + gw];
-        const int rsi = rs[j * NW + gw];
+        const int p0 = j == 0 ? p00 : par[j * NW + gw];
+        const int rsi = j == 0 ? rs00 : rs[j * NW + gw];
         int l;
         if (p0 < 0) {
           l = -p0;  // a root: already ranked
