@@ -822,7 +822,7 @@ __global__ void __launch_bounds__(REFINE_MAX_WARPS * 32)
   int* diff = (int*)(cb + WW);                                                // WW + 1: whole-word coverage, differenced
   int* rl = diff + WW + 1;                                                    // labels of the kept runs, row order
   uint32_t* rse = (uint32_t*)(rl + REFINE_RMAX);                              // start | end << 16 of the kept runs
-  const long long b = row / H;
+  const long long b = (long long)((unsigned)row / (unsigned)H);  // rows = B * H <= 65535 * 16384 < 2^31: 32-bit division
   const int y = (int)(row - b * H);
   const int NW = H * WW;
   const long long tbase = offsets ? (long long)offsets[b] : 0;
