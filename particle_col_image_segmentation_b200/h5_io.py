@@ -25,9 +25,11 @@ Usage mirrors the h5py calls of the reference::
 ``write_dataset`` writes a single-group file in the same subset (contiguous or chunked, optionally shuffle + deflate)
 -- used for the tests' fixtures and to hand images to tools that expect ilastik-style input.
 
-STATUS: no HDF5 library and no HDF5 file exists in this image, so the reader is checked against this module's own
-writer and against structures assembled field by field in the tests from the specification -- *not* against a file
-written by libhdf5.  Treat compatibility with real ilastik exports as unverified until such a file has been read.
+STATUS: no HDF5 library exists in this image, so the reader is checked against this module's own writer, against
+structures assembled field by field in the tests from the specification, and against the one libhdf5-written file
+the image holds (a MATLAB v7.3 file from scipy's test data: user block, version-0 superblock, symbol-table group,
+contiguous float64 dataset; tests/test_h5_io.py::test_reads_a_file_written_by_libhdf5).  Chunked / deflated datasets
+written by libhdf5 -- ilastik's default export layout -- have not been read yet: treat those as unverified.
 """
 
 import struct

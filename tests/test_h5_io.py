@@ -1,9 +1,13 @@
 """ilastik ``.h5`` input path (tiff_analysis.py:118-120, :639-641; refine_boundaries.py:28-31) without h5py.
 
-h5py / libhdf5 are not installable in this image and no HDF5 file exists in it, so ``h5_io.File`` is checked
-against (1) files produced by this repo's own fixture writer in every layout the reader supports and (2) the
-byte positions the HDF5 File Format Specification gives for the structures the writer emits.  Compatibility with a
-file written by libhdf5 itself is therefore NOT verified here (see the module docstring)."""
+h5py / libhdf5 are not installable in this image, so ``h5_io.File`` is checked against (1) files produced by this
+repo's own fixture writer in every layout the reader supports, (2) the byte positions the HDF5 File Format
+Specification gives for the structures the writer emits and (3) the ONE file in this image that libhdf5 itself
+wrote: scipy's MATLAB v7.3 test file (``tests/golden/libhdf5_matlab73_testdouble.mat``, a copy of
+``scipy/io/matlab/tests/data/testhdf5_7.4_GLNX86.mat``, BSD-3; MATLAB R2008 = HDF5 1.6/1.8: 512-byte user block,
+version-0 superblock, symbol-table root group, contiguous float64 dataset with attributes).  Chunked / filtered
+datasets written by libhdf5 remain unverified (no such file exists here)."""
+import os
 import struct
 
 import numpy as np
@@ -114,3 +118,24 @@ def test_newer_structures_superblock2_ohdr_links(tmp_path):
         assert list(f.keys()) == ["exported_data", "other"] and "other" in f
         assert np.array_equal(f["exported_data"][()], a) and f["exported_data"].dtype == np.int32
         assert np.array_equal(np.array(f["other"]), b)
+
+
+def test_reads_a_file_written_by_libhdf5():
+    """MATLAB v7.3 files are HDF5 files behind a 512-byte user block.  The variable of this one, ``testdouble``, is
+    0 : pi/4 : 2*pi as a 1x9 MATLAB row = a (9, 1) HDF5 dataset (MATLAB stores column-major); scipy ships the same
+    variable as a version-5 MAT file, which scipy.io.loadmat reads independently of any HDF5 code."""
+    p = os.path.join(os.path.dirname(__file__), "golden", "libhdf5_matlab73_testdouble.mat")
+    raw = open(p, "rb").read()
+    assert raw[:6] == b"MATLAB" and raw.find(b"\x89HDF\r\n\x1a\n") == 512  # the superblock is not at offset 0
+    with h5_io.File(p) as f:
+        assert list(f.keys()) == ["testdouble"]
+        ds = f["testdouble"]
+        assert ds.shape == (9, 1) and ds.dtype == np.float64
+        got = ds[()]
+    want = np.arange(0, 9) * (np.pi / 4)
+    assert np.array_equal(got[:, 0], want)
+    assert np.array_equal(h5_io.read_first_dataset(p)[:, 0], want)
+    sio = pytest.importorskip("scipy.io")
+    v5 = os.path.join(os.path.dirname(sio.__file__), "matlab", "tests", "data", "testdouble_7.4_GLNX86.mat")
+    if os.path.exists(v5):
+        assert np.array_equal(sio.loadmat(v5)["testdouble"], got.T)  # bit for bit what MATLAB wrote in the other format
