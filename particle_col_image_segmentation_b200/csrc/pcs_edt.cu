@@ -182,8 +182,17 @@ __device__ const double g_edt_sqrt_lut[EDT_LUT_N] = {
 // then written once with 16-byte coalesced stores -- 8 B/pixel of output traffic, no separate clear.
 #define EDT_TW 256
 #define EDT_HALO 40
+#ifndef EDT_TMA_FILL
+#define EDT_TMA_FILL 1  // zero fill of the float64 tile by the SM's copy engine (cp.async.bulk shared -> global, SASS UBLKCP)
+#endif
+__device__ __forceinline__ void edt_bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
+}
 #define EDT_TWH (EDT_TW + 2 * EDT_HALO)
+#ifndef EDT_ER
 #define EDT_ER 16        // rows per CTA: half a band keeps 8 CTAs (2048 threads) resident per SM
+#endif
 #define EDT_GCLAMP 255u  // vertical distances above EDT_DMAX never win a near search: 8 bits are enough
 __global__ void __launch_bounds__(EDT_TW)
     k_edt_near(const uint32_t* __restrict__ vw, const uint16_t* __restrict__ up, const uint16_t* __restrict__ dn,
@@ -222,26 +231,29 @@ __global__ void __launch_bounds__(EDT_TW)
     cub = __ldg(up + band + xb);
     cdb = __ldg(dn + band + xb);
   }
-  {
-    uint4* gz = reinterpret_cast<uint4*>(&g[0][0]);
-    for (int i = tid; i < EDT_ER * EDT_TWH / 16; i += EDT_TW) gz[i] = make_uint4(0, 0, 0, 0);
-    if (sq) {
-      uint4* dz = reinterpret_cast<uint4*>(&d2s[0][0]);
-      for (int i = tid; i < EDT_ER * EDT_TW / 8; i += EDT_TW) dz[i] = make_uint4(0, 0, 0, 0);
-    }
-  }
   // The float64 output: the whole tile is cleared here with 256-bit stores (background pixels are at
   // distance 0, and they are the majority); pass 2 then overwrites the foreground pixels one by one.  Both
   // sets of stores come from this CTA with barriers in between, so they reach memory in order and merge in
   // L2: DRAM still sees every line once.  Converting a shared tile of squared distances on the way out
   // instead cost 30 % of the kernel's instructions (four table lookups per store, predicated for all).
   const long long obase = (b * H + (q << 5) + r0) * (long long)W + x0;
-  if (dist) {
+  // full tiles: the zeros leave through the copy engine (one bulk copy of a 2 KB row segment per row, issued by one
+  // thread from a zeroed piece of shared memory).  The per-thread 256-bit stores this replaces filled the load /
+  // store queues the shared-memory traffic of the passes below goes through: stores and compute added up
+  // (155 + 47 us per 32 slices) instead of overlapping.
+  const bool bulk = EDT_TMA_FILL && dist && cols == EDT_TW && (W & 1) == 0 && ((((uintptr_t)dist) & 15) == 0);
+  if (bulk) {
+    uint4* dz = reinterpret_cast<uint4*>(&d2s[0][0]);  // 8 KB, zero from here on unless sq is asked for (pass 2)
+    for (int i = tid; i < EDT_ER * EDT_TW / 8; i += EDT_TW) dz[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy zeros before the copy engine reads them
+  } else if (dist) {
     if (cols == EDT_TW && (W & 3) == 0 && ((((uintptr_t)dist) & 31) == 0)) {
-      for (int i = tid; i < rows * (EDT_TW / 4); i += EDT_TW) {
-        double* dst = dist + obase + (long long)(i / (EDT_TW / 4)) * W + (i % (EDT_TW / 4)) * 4;
-        asm volatile("st.global.v4.f64 [%0], {%1, %1, %1, %1};" ::"l"(dst), "d"(0.0) : "memory");
-      }
+      // thread = (row tid / 64 of every group of four rows, four columns): one pointer, a constant stride
+      double* dst = dist + obase + (long long)(tid >> 6) * W + ((tid & 63) << 2);
+      const long long step = 4ll * W;
+#pragma unroll
+      for (int r = tid >> 6; r < EDT_ER; r += EDT_TW / 64, dst += step)
+        if (r < rows) asm volatile("st.global.v4.f64 [%0], {%1, %1, %1, %1};" ::"l"(dst), "d"(0.0) : "memory");
     } else {
       for (int i = tid; i < rows * EDT_TW; i += EDT_TW) {
         const int r = i / EDT_TW, c = i % EDT_TW;
@@ -249,7 +261,48 @@ __global__ void __launch_bounds__(EDT_TW)
       }
     }
   }
-  __syncthreads();
+  // this CTA's rows of the two column words; a tile whose own columns hold no foreground (the halo only lends its g
+  // to pixels of the tile) is done once its zeros are on their way -- most tiles of a blob image: no shared tiles
+  // to clear, no lists, no further barriers
+  const uint32_t rmask = (rows < 32 ? (1u << rows) - 1u : 0xffffffffu) & ((EDT_ER == 32) ? 0xffffffffu : ((1u << EDT_ER) - 1u));
+  const uint32_t fra = (fa >> r0) & rmask, frb = (fb >> r0) & rmask;  // zero where the column is outside the image
+  const uint32_t own = tid >= EDT_HALO ? fra : frb;  // slot 0 holds columns -HALO .. TW-HALO-1 of the tile, slot 1 the rest
+  const int any = __syncthreads_or(own != 0u);
+  if (bulk && tid == 0) {
+    for (int r = 0; r < rows; ++r) edt_bulk_store(dist + obase + (long long)r * W, &d2s[0][0], EDT_TW * 8);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+  if (!any && !sq && !thr_bits) {
+    // shared memory must outlive the copy engine's reads of it
+    if (bulk && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    return;
+  }
+  {
+    // g = 0 for the columns of the image, EDT_GCLAMP (no site) for tile or halo columns outside it
+    uint4* gz = reinterpret_cast<uint4*>(&g[0][0]);
+    for (int i = tid; i < EDT_ER * EDT_TWH / 16; i += EDT_TW) {
+      const int xl = x0 - EDT_HALO + (i % (EDT_TWH / 16)) * 16;  // image column of the first of these 16 bytes
+      uint4 z = make_uint4(0, 0, 0, 0);
+      if (xl < 0 || xl + 15 >= W) {
+        uint32_t wv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          wv[k] = 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int x = xl + 4 * k + j;
+            if (x < 0 || x >= W) wv[k] |= EDT_GCLAMP << (8 * j);
+          }
+        }
+        z = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+      }
+      gz[i] = z;
+    }
+    if (sq && !bulk) {
+      uint4* dz = reinterpret_cast<uint4*>(&d2s[0][0]);
+      for (int i = tid; i < EDT_ER * EDT_TW / 8; i += EDT_TW) dz[i] = make_uint4(0, 0, 0, 0);
+    }
+  }
   // pass 1a, thread per column: list the foreground pixels of tile + halo (warp-level exclusive scan of the
   // per-column counts) and park the column's word and carries in shared memory
 #pragma unroll
@@ -257,19 +310,15 @@ __global__ void __launch_bounds__(EDT_TW)
     if (slot == 1 && tid >= 2 * EDT_HALO) break;
     const int col = tid + slot * EDT_TW;
     const uint32_t fw = slot ? fb : fa;
-    uint32_t f = (fw >> r0) & ((EDT_ER == 32) ? 0xffffffffu : ((1u << EDT_ER) - 1u));  // this CTA's rows of the column
-    if (rows < EDT_ER) f &= (1u << rows) - 1u;
+    const uint32_t f = slot ? frb : fra;
     if (slot ? inb : ina) {
       zcol[col] = ~fw;
       cucol[col] = (unsigned short)(slot ? cub : cua);
       cdcol[col] = (unsigned short)(slot ? cdb : cda);
-    } else {
-      f = 0;
-#pragma unroll 8
-      for (int r = 0; r < EDT_ER; ++r) g[r][col] = (uint8_t)EDT_GCLAMP;  // outside the image: no site
     }
     const int cnt = __popc(f);
     const unsigned act = __activemask();
+    if (__ballot_sync(act, cnt != 0) == 0u) continue;  // none of this warp's columns holds foreground (warp-uniform)
     int incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -279,7 +328,7 @@ __global__ void __launch_bounds__(EDT_TW)
     const int last = 31 - __clz(act);
     int wtot = __shfl_sync(act, incl, last);
     int wbase = 0;
-    if ((tid & 31) == last && wtot) wbase = atomicAdd(&nitems, wtot);
+    if ((tid & 31) == last) wbase = atomicAdd(&nitems, wtot);
     wbase = __shfl_sync(act, wbase, last);
     if (cnt) {
       int pos = wbase + incl - cnt;
@@ -300,6 +349,8 @@ __global__ void __launch_bounds__(EDT_TW)
     const int r = item >> 9, c = item & 511;
     g[r][c] = (uint8_t)min(edt_vdist(zcol[c], r0 + r, cucol[c], cdcol[c]), EDT_GCLAMP);
   }
+  // pass 2 overwrites foreground pixels of the tile (and d2s when sq is asked for): the zeros must have landed first
+  if (bulk && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   __syncthreads();
   if (thr_bits) {
     // background pixels are at distance 0: start every row word from them (warp w owns word w)
