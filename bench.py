@@ -67,13 +67,13 @@ KERNEL_BYTES_PER_VOXEL = {
 # when the kernel ends.
 NCU_TRAFFIC_SOURCE = "profiles/r2_ncu_full_summary.txt"
 NCU_TRAFFIC_BYTES_PER_VOXEL = {
-    "k_edt_near": (16.81 + 481.00) / 67.109,
-    "k_hist_u16": (136.05 + 4.40) / 67.109,
-    "k_seg_threshold_tile": (142.27 + 63.14) / 67.109,
-    "k_ccl_relabel": (18.30 + 209.95) / 67.109,
-    "k_refine_rows": (18.48 + 25.62) / 67.109,
+    "k_edt_near": (16.81 + 481.60) / 67.109,
+    "k_hist_u16": (136.03 + 4.01) / 67.109,
+    "k_seg_threshold_tile": (142.32 + 59.99) / 67.109,
+    "k_ccl_relabel": (18.31 + 210.57) / 67.109,
+    "k_refine_rows": (18.48 + 25.75) / 67.109,
 }
-NCU_TRAFFIC_WHOLE_STEP_BYTES_PER_VOXEL = (431.3 + 784.2) / 67.109  # every kernel of the step: 18.1 B/voxel (round 1: 21.8; algorithmic: 16)
+NCU_TRAFFIC_WHOLE_STEP_BYTES_PER_VOXEL = (431.3 + 782.0) / 67.109  # every kernel of the step: 18.1 B/voxel (round 1: 21.8; algorithmic: 16)
 
 
 def write_only_probe(dev, lib):
