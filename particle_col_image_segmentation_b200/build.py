@@ -77,7 +77,8 @@ def build(force=False, verbose=False, variant=None, extra_flags=()):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed building libpcs.so")
-    subprocess.check_call([NVCC, "-shared", "-o", lib, *objs, "-lcudart"])
+    # the link step gets the arch too: without it nvcc adds an (empty) device-link stub for its default sm_52
+    subprocess.check_call([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib, *objs, "-lcudart"])
     if not variant:
         with open(LIB + ".hash", "w") as f:
             f.write(source_hash() + "\n")

@@ -181,3 +181,29 @@ def test_bench_reference_arm_contract():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     out1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True, text=True, timeout=120, env=env)
     assert out1.returncode == 0 and out1.stdout.strip() == ""
+
+
+def test_built_library_is_sm100a_with_copy_engine_fill():
+    """The shipped libpcs.so holds sm_100a code only, and the dominant kernel's zero fill goes through the SM's copy
+    engine (cp.async.bulk shared -> global = SASS UBLKCP.G.S; DESIGN.md section 4c, profiles/r2_tma_ab.txt)."""
+    import shutil
+
+    from particle_col_image_segmentation_b200 import _lib
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    _lib.load()
+    lib = os.path.join(ROOT, "particle_col_image_segmentation_b200", "libpcs.so")
+    elf = subprocess.run([cuobjdump, "-lelf", lib], capture_output=True, text=True, timeout=300).stdout
+    archs = set(re.findall(r"sm_\d+a?", elf))
+    assert archs == {"sm_100a"}, archs
+    sass = subprocess.run([cuobjdump, "-sass", lib], capture_output=True, text=True, timeout=600).stdout
+    per_fn, fn = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            fn = m.group(1)
+        elif fn and "UBLKCP.G.S" in line:
+            per_fn[fn] = per_fn.get(fn, 0) + 1
+    assert any("k_edt_near" in f for f in per_fn), f"k_edt_near no longer stores through the copy engine: {per_fn}"
