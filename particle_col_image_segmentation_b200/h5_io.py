@@ -543,13 +543,39 @@ def write_dataset(path, arrays, chunks=None, compression=None, shuffle=False):
                     elif fid == 1:
                         raw = zlib.compress(raw, cd[0])
                 entries.append((len(raw), [int(o) for o in offs], put(raw)))
-            if len(entries) > 64:
-                raise H5Error("the fixture writer keeps the chunk index in one B-tree node: at most 64 chunks")
-            node = bytearray(b"TREE" + bytes([1, 0]) + struct.pack("<HQQ", len(entries), UNDEF, UNDEF))
-            for size, offs, addr in entries:
-                node += struct.pack("<II", size, 0) + b"".join(struct.pack("<Q", o) for o in offs) + struct.pack("<Q", 0) + struct.pack("<Q", addr)
-            node += struct.pack("<II", 0, 0) + b"".join(struct.pack("<Q", s) for s in a.shape) + struct.pack("<Q", 0)  # final key
-            btree_at = put(bytes(node))
+            # version-1 B-tree of the chunks: leaves of at most 64 entries (libhdf5's default 2K for chunk trees),
+            # internal levels above them while one level holds more than one node; a node's key i is the key of the
+            # left-most chunk under child i, its last key the upper bound (the dataset shape for the right-most node)
+            def key(size, offs):
+                return struct.pack("<II", size, 0) + b"".join(struct.pack("<Q", o) for o in offs) + struct.pack("<Q", 0)
+
+            level, nodes = 0, [(e[0], e[1], e[2]) for e in entries]  # (size, offsets, address) of chunks, then of nodes
+            end_key = key(0, list(a.shape))
+            while True:
+                groups = [nodes[i : i + 64] for i in range(0, len(nodes), 64)] or [[]]
+                bodies = []
+                for gi, grp in enumerate(groups):
+                    body = bytearray()
+                    for size, offs, addr in grp:
+                        body += key(size, offs) + struct.pack("<Q", addr)
+                    nxt = groups[gi + 1][0] if gi + 1 < len(groups) else None
+                    body += key(nxt[0], nxt[1]) if nxt else end_key
+                    bodies.append(body)
+                # sibling addresses: the nodes of a level are written back to back, so they are known up front
+                sizes = [24 + len(bd) for bd in bodies]
+                base = put(b"")  # aligned position of the level's first node
+                starts = [base + sum(sizes[:i]) for i in range(len(sizes))]
+                written = []
+                for gi, (grp, bd) in enumerate(zip(groups, bodies)):
+                    left = starts[gi - 1] if gi > 0 else UNDEF
+                    right = starts[gi + 1] if gi + 1 < len(groups) else UNDEF
+                    at = put(b"TREE" + bytes([1, level]) + struct.pack("<HQQ", len(grp), left, right) + bytes(bd))
+                    assert at == starts[gi]
+                    written.append((grp[0][0] if grp else 0, grp[0][1] if grp else [0] * a.ndim, at))
+                if len(written) == 1:
+                    btree_at = written[0][2]
+                    break
+                level, nodes = level + 1, written
             msgs.append(_msg(0x08, struct.pack("<BBBQ", 3, 2, a.ndim + 1, btree_at) + b"".join(struct.pack("<I", c) for c in cshape) + struct.pack("<I", dt.itemsize)))
             if pipeline:
                 fl = struct.pack("<BB6x", 1, len(pipeline))

@@ -139,3 +139,20 @@ def test_reads_a_file_written_by_libhdf5():
     v5 = os.path.join(os.path.dirname(sio.__file__), "matlab", "tests", "data", "testdouble_7.4_GLNX86.mat")
     if os.path.exists(v5):
         assert np.array_equal(sio.loadmat(v5)["testdouble"], got.T)  # bit for bit what MATLAB wrote in the other format
+
+
+@pytest.mark.parametrize("compression", [None, "gzip"])
+def test_multi_level_chunk_btree(tmp_path, compression):
+    """A 2048^2 ilastik export in 64x64 chunks has 1024 chunks: libhdf5 keeps at most 64 entries in a chunk B-tree node,
+    so real files carry trees of two and more levels.  150 x 70 chunks of 8x8 = 10 500 chunks -> three levels."""
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 4, (1, 1200, 560), dtype=np.uint8)
+    p = h5_io.write_dataset(str(tmp_path / "deep.h5"), a, chunks=(1, 8, 8), compression=compression)
+    raw = open(p, "rb").read()
+    levels = {raw[i + 5] for i in range(0, len(raw) - 8, 8) if raw[i : i + 4] == b"TREE" and raw[i + 4] == 1}
+    assert levels == {0, 1, 2}
+    with h5_io.File(p) as f:
+        assert np.array_equal(f["exported_data"][()], a)
+    b = rng.random((130, 70)).astype(np.float32)  # two levels, ragged edge chunks
+    q = h5_io.write_dataset(str(tmp_path / "two.h5"), b, chunks=(8, 8), compression=compression, shuffle=bool(compression))
+    assert np.array_equal(h5_io.read_first_dataset(q), b)
